@@ -1,0 +1,214 @@
+/*
+ * wssdl_b200.h -- C ABI of libwssdl_b200.so: the B200 (sm_100a) implementation of the
+ * detector hot path of syshin1014/wssdl_bus.
+ *
+ * Every entry point replaces one native/Cython interface of the reference (cited per
+ * function, paths relative to the reference's code/lib).  Conventions for all DEVICE
+ * entry points:
+ *   - pointers are device pointers owned by the caller (no hidden allocation);
+ *   - work is enqueued on `stream` and the call returns without synchronising;
+ *   - the return value is WSSDL_OK or a negative WSSDL_E* code / positive cudaError_t;
+ *     nothing ever calls exit() (the reference does: roi_pooling_op_gpu.cu.cc:102-107);
+ *   - scratch memory is passed in as `workspace` sized by the matching *_workspace_bytes.
+ * The *_host entry points take HOST pointers, are synchronous and manage their own
+ * device scratch, like the reference's `_nms` (nms/gpu_nms.hpp:1-2).
+ *
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef WSSDL_B200_H_
+#define WSSDL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cudaStream_t without including cuda_runtime.h in client code */
+typedef struct CUstream_st* wssdl_stream_t;
+
+enum {
+  WSSDL_OK = 0,
+  WSSDL_EINVAL = -1,     /* bad argument (negative size, null pointer, ...)            */
+  WSSDL_EWORKSPACE = -2, /* workspace too small                                       */
+  WSSDL_EALIGN = -3,     /* pointer not aligned as documented                         */
+  WSSDL_ELIMIT = -4,     /* size beyond what the kernels support                      */
+  WSSDL_EZERODIV = -5    /* host NMS: a box pair with zero union (reference raises    */
+                         /* ZeroDivisionError, nms/cpu_nms.c:2480-2483)               */
+};
+
+int wssdl_version(void);                    /* 100 * major + minor */
+const char* wssdl_error_string(int code);   /* static string, also for cudaError_t codes */
+
+/* ---------------------------------------------------------------- RoI max pooling
+ * Replaces ROIPoolForwardLaucher / ROIPoolBackwardLaucher
+ * (roi_pooling_layer/roi_pooling_op_gpu.h:18-27) and the CPU op bodies
+ * RoiPoolOp<CPUDevice>::Compute / RoiPoolGradOp<CPUDevice>::Compute
+ * (roi_pooling_layer/roi_pooling_op.cc:88-204, :333-466).
+ *
+ * bottom      [B,H,W,C] f32 NHWC        rois   [R,5] f32 (batch, x1, y1, x2, y2) image px
+ * top, argmax [R,PH,PW,C] f32 / i32;    argmax = per-image flat index (h*W+w)*C+c, -1 if
+ *             the bin is empty; argmax may be NULL (roi_pooling_op_gpu.cu.cc:82-83).
+ * bin_mode    WSSDL_BIN_CPU_TRUNC reproduces the CPU op (roi_pooling_op.cc:167-170, the
+ *             parity target: int cast BEFORE floor/ceil, bins never overlap);
+ *             WSSDL_BIN_GPU_CEIL reproduces the CUDA op (roi_pooling_op_gpu.cu.cc:51-58).
+ * A RoI whose batch index is outside [0,B) yields top=0/argmax=-1 (the reference reads
+ * out of bounds).  16-byte aligned pointers and C%4==0 select the vectorised kernels;
+ * anything else runs the scalar variant of the same kernel.
+ */
+enum { WSSDL_BIN_CPU_TRUNC = 0, WSSDL_BIN_GPU_CEIL = 1 };
+
+int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B, int H, int W, int C,
+                       int R, int PH, int PW, float spatial_scale, int bin_mode,
+                       float* top, int* argmax, wssdl_stream_t stream);
+
+/* bwd_mode WSSDL_BWD_ATOMIC: zero-fill + scatter through argmax with fp32 atomics
+ *            (fast; summation order free => equal to the reference within 1e-5 rel;
+ *            global fp32 atomics flush subnormals);
+ *          WSSDL_BWD_GATHER: deterministic gather, one CTA per input cell, additions in
+ *            the reference's order (roi, ph, pw ascending) => bit-exact.
+ * Both apply the reference's in-RoI and feasible-bin tests (roi_pooling_op.cc:415-445), so
+ * the result equals the reference's for ANY argmax tensor, not only one produced by the
+ * forward pass (e.g. malformed RoIs with x2<x1 contribute nothing).
+ */
+enum { WSSDL_BWD_ATOMIC = 0, WSSDL_BWD_GATHER = 1 };
+
+int wssdl_roi_pool_bwd(const float* top_diff, const int* argmax, const float* rois, int B,
+                       int H, int W, int C, int R, int PH, int PW, float spatial_scale,
+                       int bwd_mode, float* bottom_diff, wssdl_stream_t stream);
+
+/* ---------------------------------------------------------------- greedy NMS
+ * Replaces cpu_nms (nms/cpu_nms.pyx:17-68), utils.cython_nms.nms / nms_new
+ * (utils/nms.pyx:17-68, :70-123), gpu_nms + _nms (nms/gpu_nms.pyx:16-31,
+ * nms/nms_kernel.cu:91-144) and py_cpu_nms (nms/py_cpu_nms.py:10-38).
+ *
+ * dets [N,dets_stride] f32 rows (x1,y1,x2,y2,score,...), dets_stride >= 5.
+ * Sorts on the device by (score desc, index desc) -- the order of
+ * `scores.argsort(kind='stable')[::-1]`; the reference uses numpy's default unstable
+ * argsort, so tie order is only defined for unique scores -- then runs the 64-bit bitmask
+ * pass over the upper triangle and an on-device sweep.  keep[0..*num_keep) receives
+ * indices into the ORIGINAL array in descending-score order, exactly `order[keep]`.
+ *
+ * mode   WSSDL_NMS_GE_F64: suppress iff (double)iou_f32 >= thresh   (cpu_nms.pyx:65 with a
+ *                          Python-float thresh: cpu_nms.c:2492-2495)
+ *        WSSDL_NMS_GT_F32: suppress iff iou_f32 > (float)thresh     (nms_kernel.cu:71,
+ *                          py_cpu_nms.py:35)
+ *        | WSSDL_NMS_CONTAIN: additionally suppress when inter/area_i > 0.95 or
+ *                          inter/area_j > 0.95                       (nms_new, nms.pyx:117-120)
+ * max_keep  stop after this many kept boxes (<=0: no limit); keep must hold
+ *           min(N, max_keep>0 ? max_keep : N) ints.
+ * status    device int[2] (may be NULL): [0] = 1 if some pair had a zero union.
+ */
+enum { WSSDL_NMS_GE_F64 = 0, WSSDL_NMS_GT_F32 = 1, WSSDL_NMS_CONTAIN = 4 };
+
+size_t wssdl_nms_workspace_bytes(int N);
+
+int wssdl_nms(const float* dets, int N, int dets_stride, double thresh, int mode,
+              int max_keep, int* keep, int* num_keep, int* status, void* workspace,
+              size_t workspace_bytes, wssdl_stream_t stream);
+
+/* Host-pointer twins.  wssdl_gpu_nms_host has the argument list of the reference's
+ * `_nms` (nms/gpu_nms.hpp:1-2: boxes already sorted by descending score, `>` against a
+ * float threshold, keep_out = positions in the sorted array) and can be bound in its
+ * place; wssdl_nms_host is the cpu_nms-shaped call (unsorted dets, double threshold,
+ * `>=`, keep_out = original indices). */
+int wssdl_gpu_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num,
+                       int boxes_dim, float nms_overlap_thresh, int device_id);
+int wssdl_nms_host(int* keep_out, int* num_out, const float* dets_host, int N,
+                   int dets_stride, double thresh, int mode, int max_keep, int device_id);
+
+/* ---------------------------------------------------------------- IoU matrices
+ * Replaces bbox_overlaps (utils/bbox.pyx:15-55) and bbox_overlaps_ui
+ * (utils/bbox_ui.pyx:12-46).  boxes [N,4], query [K,4] -> out [N,K], row major.
+ * kind WSSDL_IOU: intersection over union (+1 convention); WSSDL_IOU_UI: intersection
+ * over area(boxes[n]).  The f64 entry evaluates the reference's expression tree with one
+ * rounding per operation (no FMA) and is bit-exact; the f32 entry is the fast variant.
+ */
+enum { WSSDL_IOU = 0, WSSDL_IOU_UI = 1 };
+
+int wssdl_bbox_overlaps_f64(const double* boxes, int N, const double* query, int K, int kind,
+                            double* out, wssdl_stream_t stream);
+int wssdl_bbox_overlaps_f32(const float* boxes, int N, const float* query, int K, int kind,
+                            float* out, wssdl_stream_t stream);
+
+/* ---------------------------------------------------------------- box transforms
+ * Replaces bbox_transform_inv / clip_boxes / bbox_transform
+ * (fast_rcnn/bbox_transform.py:30-61, :63-77, :10-28), fp32.
+ * boxes [N,4]; deltas/out [N,4*k] (class-major groups of 4, :41-44).
+ * exp() is evaluated in fp64 and rounded once to fp32 (correctly rounded); numpy's SIMD
+ * expf is within 1 ulp of that, hence the 1e-5 relative tolerance on decoded boxes.
+ */
+int wssdl_bbox_transform_inv(const float* boxes, const float* deltas, int N, int k,
+                             float* out, wssdl_stream_t stream);
+int wssdl_clip_boxes(float* boxes, int N, int k, float im_h, float im_w,
+                     wssdl_stream_t stream);
+int wssdl_bbox_transform(const float* ex_rois, const float* gt_rois, int N, float* targets,
+                         wssdl_stream_t stream);
+
+/* ---------------------------------------------------------------- RPN proposals
+ * Replaces proposal_layer (rpn_msr/proposal_layer_tf_bus.py:19-148): anchors generated on
+ * the fly (generate_anchors.py:37-97 + shifts :55-71), bbox_transform_inv, clip_boxes,
+ * _filter_boxes (:151-156), score sort + pre-NMS top-N (:129-133), NMS (:138), post-NMS
+ * top-N (:139-146), batched over images: one CTA per image, everything in shared memory.
+ *
+ * cls_prob  [B,H,W,2A] f32 NHWC (fg score of anchor a = channel A+a, :86)
+ * bbox_pred [B,H,W,4A] f32 NHWC (deltas of anchor a = channels 4a..4a+3, :106)
+ * im_info   [B,info_stride] f32 rows (im_h, im_w, im_scale, ...)
+ * base_anchors [A,4] f32, HOST pointer (integer valued; generate_anchors output, A <= 32;
+ *           it is copied into the kernel's parameter block)
+ * rois      [B*post_nms_topN,5] f32: image b owns rows [b*post, b*post+counts[b]);
+ *           rows (b, x1,y1,x2,y2); unused rows are zero-filled
+ * scores    [B*post_nms_topN] f32 (may be NULL), anchor_idx [B*post_nms_topN] i32 (may be
+ *           NULL): the (h,w,a) anchor each RoI came from
+ * counts    [B] i32
+ * decoded   [B,H*W*A,4] f32 (may be NULL): every anchor decoded+clipped, row order (h,w,a)
+ *           -- the intermediate of :116-119, for inspection and parity tests
+ * pre_nms_topN <= 0 means "no truncation" (:130).
+ * Limits (WSSDL_ELIMIT otherwise): H*W*A <= 32768 anchors per image, 0 < post_nms_topN <=
+ * 4096, and the per-image state must fit one SM's shared memory:
+ * 8*pow2ceil(min(pre_nms_topN, H*W*A)) + 4*H*W*A + 20*post_nms_topN + 16 KB <= 227 KB
+ * (the reference's shapes: 17100 anchors with 6000->300 or 12000->2000 fit).
+ */
+size_t wssdl_proposals_workspace_bytes(int B, int H, int W, int A, int pre_nms_topN,
+                                       int post_nms_topN);
+
+int wssdl_proposals(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                    int info_stride, int B, int H, int W, int A, const float* base_anchors,
+                    int feat_stride, int pre_nms_topN, int post_nms_topN, double nms_thresh,
+                    float min_size, float* rois, float* scores, int* anchor_idx, int* counts,
+                    float* decoded, void* workspace, size_t workspace_bytes,
+                    wssdl_stream_t stream);
+
+/* ---------------------------------------------------------------- anchor labelling
+ * Replaces the deterministic part of anchor_target_layer[_joint]
+ * (rpn_msr/anchor_target_layer_tf_bus.py:410-509): inside filter, fp64 IoU against the
+ * foreground GT rows, uni-directional overlap against the background GT rows, labels.
+ * Batched over images; the npr.choice subsampling (:512-527) stays on the host.
+ *
+ * gt_boxes [B,max_gt,5] f32 (x1,y1,x2,y2,cls), fg rows (cls != 0) first (:434-436);
+ * num_gt [B] i32; base_anchors [A,4] f32 HOST pointer.
+ * dataset_mode 0: 'SNUBH' (:430-468, explicit background boxes label anchors 0 when their
+ *                 uni-directional overlap >= positive_overlap);
+ *              1: 'SNUBH_FG' (:470-477, fg rows only) ; 2: other datasets (all rows are fg);
+ *                 modes 1,2 use the classic rules with negative_overlap (:497-509).
+ * labels [B,H*W*A] f32 in (h,w,a) order: 1 fg, 0 bg, -1 don't care (anchors not inside
+ * the image are -1, as after _unmap :568); argmax_gt [B,H*W*A] i32 = row of the best fg GT
+ * (first maximum, -1 outside); max_overlap [B,H*W*A] f64 (may be NULL).
+ * An image without fg rows yields no positives (the reference raises in argmax there).
+ * Limits: A <= 32, max_gt <= 64, B <= 65535.
+ */
+size_t wssdl_anchor_labels_workspace_bytes(int B, int H, int W, int A, int max_gt);
+
+int wssdl_anchor_labels(const float* gt_boxes, const int* num_gt, int max_gt,
+                        const float* im_info, int info_stride, int B, int H, int W, int A,
+                        const float* base_anchors, int feat_stride, int dataset_mode,
+                        double positive_overlap, double negative_overlap,
+                        int clobber_positives, float* labels, int* argmax_gt,
+                        double* max_overlap, void* workspace, size_t workspace_bytes,
+                        wssdl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSSDL_B200_H_ */

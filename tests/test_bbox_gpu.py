@@ -1,0 +1,116 @@
+"""IoU matrices (fp64 bit-exact), box transforms (1e-5 relative) and anchor labels
+(bit-exact) on the GPU against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from wssdl_bus_b200 import ops, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # north star: decoded boxes / IoU within 1e-5 relative
+
+
+def test_iou_golden_bit_exact(golden):
+    b, q = golden["iou_boxes"], golden["iou_query"]
+    assert np.array_equal(ops.bbox_overlaps(b, q), golden["iou_out"])
+    assert np.array_equal(ops.bbox_overlaps_ui(b, q), golden["iou_ui_out"])
+
+
+@pytest.mark.parametrize("N,K", [(0, 5), (5, 0), (1, 1), (17100, 20), (5944, 3), (2020, 20),
+                                 (10000, 1024), (3000, 1500)])
+def test_iou_vs_oracle_bit_exact(oracle_mod, N, K):
+    b = syn.random_boxes(400 + N, N).astype(np.float64)
+    q = syn.random_boxes(401 + K, K, lo=30, hi=300).astype(np.float64)
+    got = ops.bbox_overlaps(b, q)
+    assert got.dtype == np.float64 and got.shape == (N, K)
+    assert np.array_equal(got, oracle_mod.clib.bbox_overlaps(b, q))
+    assert np.array_equal(ops.bbox_overlaps_ui(b, q), oracle_mod.clib.bbox_overlaps(b, q, ui=True))
+
+
+def test_iou_f32_fast_variant_and_properties(oracle_mod):
+    b = syn.random_boxes(410, 4000)
+    q = syn.random_boxes(411, 128)
+    want = oracle_mod.clib.bbox_overlaps(b.astype(np.float64), q.astype(np.float64))
+    got = ops.bbox_overlaps_device(b, q, ops.IOU, torch.float32).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-6)
+    # C5-scale N x N: symmetry + unit diagonal, size-independent
+    n = 20000
+    bb = torch.from_numpy(syn.random_boxes(412, n).astype(np.float64)).cuda()
+    m = ops.bbox_overlaps_device(bb, bb[:2048], ops.IOU, torch.float64)
+    assert bool(torch.all(m[:2048].diagonal() == 1.0))
+    assert bool(torch.equal(m[:2048], m[:2048].t()))
+    assert float(m.min()) >= 0.0 and float(m.max()) <= 1.0
+
+
+def test_bbox_transform_golden(golden):
+    inv = ops.bbox_transform_inv(golden["bt_boxes"], golden["bt_deltas"])
+    assert inv.dtype == np.float32 and inv.shape == golden["bt_inv"].shape
+    np.testing.assert_allclose(inv, golden["bt_inv"], rtol=RTOL, atol=1e-4)
+    clipped = ops.clip_boxes(golden["bt_inv"].copy(), (600, 800))
+    assert np.array_equal(clipped, golden["bt_clip"])                      # exact: min/max only
+    assert np.array_equal(ops.clip_boxes(clipped.copy(), (600, 800)), clipped)   # idempotent
+    t = ops.bbox_transform(golden["bt_ex"], golden["bt_gt"])
+    np.testing.assert_allclose(t, golden["bt_targets"], rtol=RTOL, atol=1e-6)
+    assert ops.bbox_transform_inv(np.zeros((0, 4)), np.zeros((0, 12), np.float32)).shape == (0, 12)
+
+
+@pytest.mark.parametrize("dataset,mode", [("SNUBH", 0), ("SNUBH_FG", 1), ("UDIAT", 2)])
+def test_anchor_labels_bit_exact(oracle_mod, dataset, mode):
+    B, H, W = 4, 38, 50
+    gt, num = syn.gt_boxes(500, B)
+    info = np.tile(np.array([[600, 800, 1.0]], np.float32), (B, 1))
+    from wssdl_bus_b200.rpn_msr.generate_anchors import generate_anchors
+    base = generate_anchors(scales=np.array([8, 16, 32]))
+    labels, argmax, maxov = ops.anchor_labels(gt, num, info, H, W, base, 16, dataset_mode=mode)
+    labels, argmax, maxov = labels.cpu().numpy(), argmax.cpu().numpy(), maxov.cpu().numpy()
+    for b in range(B):
+        lab = oracle_mod.layers.anchor_labels(H, W, gt[b, :num[b]], info[b], dataset=dataset)
+        ins = lab["inds_inside"]
+        assert len(ins) == 5944                                   # SURVEY probe for 600x800
+        full = np.full(H * W * 9, -1, np.float32)
+        full[ins] = lab["labels"]
+        assert np.array_equal(labels[b], full)
+        assert np.array_equal(argmax[b][ins], lab["argmax_overlaps"])
+        assert np.all(np.delete(argmax[b], ins) == -1)
+        assert np.array_equal(maxov[b][ins], lab["max_overlaps"])
+        assert (lab["labels"] == 1).sum() > 0
+
+
+def test_anchor_and_proposal_target_layers_match_oracle(oracle_mod):
+    """Full layers with the host RNG seeded identically on both sides."""
+    import numpy.random as npr
+    from wssdl_bus_b200.rpn_msr import anchor_target_layer_tf_bus as atl
+    from wssdl_bus_b200.rpn_msr import proposal_target_layer_tf_bus as ptl
+    H, W, A = 38, 50, 9
+    gt, num = syn.gt_boxes(510, 1)
+    info = np.array([[600, 800, 1.0]], np.float32)
+    score = np.zeros((1, H, W, 2 * A), np.float32)
+    npr.seed(3)
+    lab, tgt, iw, ow = atl.anchor_target_layer(score, gt, num, info, None, [16, ], [8, 16, 32], "SNUBH")
+    npr.seed(3)
+    o = oracle_mod.layers.anchor_labels(H, W, gt[0, :num[0]], info[0], dataset="SNUBH")
+    ol, ot, oiw, oow = oracle_mod.layers.anchor_targets_from_labels(o, npr)
+    want_lab = ol.reshape((1, H, W, A)).transpose(0, 3, 1, 2).reshape((1, 1, A * H, W))
+    assert lab.shape == (1, 1, A * H, W) and np.array_equal(lab, want_lab)
+    want_t = ot.reshape((1, H, W, A * 4)).transpose(0, 3, 1, 2)
+    np.testing.assert_allclose(tgt, want_t, rtol=RTOL, atol=1e-6)
+    assert np.array_equal(iw, oiw.reshape((1, H, W, A * 4)).transpose(0, 3, 1, 2))
+    np.testing.assert_allclose(ow, oow.reshape((1, H, W, A * 4)).transpose(0, 3, 1, 2), rtol=1e-6)
+    # joint flavour: 1 supervised + 2 weakly supervised images
+    lab3, t3, _, _ = atl.anchor_target_layer_joint(np.zeros((3, H, W, 2 * A), np.float32),
+                                                   np.tile(gt, (3, 1, 1)), np.tile(num, 3),
+                                                   np.tile(info, (3, 1)), None, True, [16, ],
+                                                   [8, 16, 32], "SNUBH")
+    assert lab3.shape == (3, 1, A * H, W) and np.all(lab3[1:] == -1) and not t3[1:].any()
+    # proposal target layer
+    rois = syn.rois_for_pool(511, 300)
+    npr.seed(4)
+    r, l, t, iw2, ow2 = ptl.proposal_target_layer(rois, gt, num, 3, True, False)
+    npr.seed(4)
+    pos = gt[0, :int((gt[0, :num[0], 4] != 0).sum())]
+    allr = np.vstack((rois, np.hstack((np.zeros((len(pos), 1), np.float32), pos[:, :4]))))
+    ol, orois, ot, oiw, _ = oracle_mod.layers.sample_rois(allr, pos, 32, 128, 3, npr)
+    assert np.array_equal(r, orois) and np.array_equal(l.ravel(), ol)
+    np.testing.assert_allclose(t, ot, rtol=RTOL, atol=1e-6)
+    assert np.array_equal(iw2, oiw) and np.array_equal(ow2, (oiw > 0).astype(np.float32))

@@ -1,0 +1,46 @@
+"""world_size-2 gloo test of the only collective on the path: the all-gather of per-image
+detections, plus the image sharding / un-sharding bookkeeping (no GPU)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_images, post, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from wssdl_bus_b200.pipeline import all_gather_detections, shard_images, unshard_detections
+    mine = shard_images(n_images, rank, world)
+    n_local = (n_images + world - 1) // world
+    det = torch.zeros((n_local, post, 5))
+    cnt = torch.zeros((n_local,), dtype=torch.int32)
+    for j, img in enumerate(mine):                      # fake detections tagged by image id
+        det[j, :, 0] = float(img)
+        det[j, :, 4] = torch.arange(post, 0, -1)
+        cnt[j] = int(img) % post + 1
+    det_all, cnt_all = all_gather_detections(det, cnt)
+    d, c = unshard_detections(det_all, cnt_all, n_images)
+    ok = d.shape == (n_images, post, 5) and all(float(d[i, 0, 0]) == i for i in range(n_images))
+    ok = ok and c.tolist() == [i % post + 1 for i in range(n_images)]
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_all_gather_detections_gloo_world2():
+    world, n_images, post = 2, 7, 4
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n_images, post, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

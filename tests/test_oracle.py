@@ -1,0 +1,200 @@
+"""Pin the CPU oracle (no GPU): C restatement vs the reference's own compiled Cython
+(oracle/_ref), vs fixtures generated from the reference (tests/golden), vs the reference's
+bbox_transform.py loaded by path, and vs the hand-derived RoI-pool bin tables of SURVEY.md
+Appendix A.1 (the reference has no RoI-pool test vectors at all)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE_PRESENT
+from wssdl_bus_b200 import synthetic as syn
+
+
+def test_anchor_table_golden(oracle_mod, golden):
+    # the only golden vector the reference ships: generate_anchors.py:17-25 (1-based)
+    a = oracle_mod.layers.generate_anchors()
+    assert np.array_equal(a, golden["anchors_table_minus_1"])
+
+
+@pytest.mark.parametrize("key", ["nms_uni_257", "nms_uni_1000", "nms_clu_257", "nms_clu_1000",
+                                 "nms_fork"])
+def test_c_nms_matches_reference_golden(oracle_mod, golden, key):
+    d = golden[key + "_dets"]
+    for t in (0.3, 0.5, 0.7):
+        want = golden[key + "_keep_%02d" % int(t * 10)].tolist()
+        assert oracle_mod.clib.nms(d, t) == want
+    if key + "_keepnew_05" in golden:
+        assert oracle_mod.clib.nms(d, 0.5, variant=1) == golden[key + "_keepnew_05"].tolist()
+
+
+def test_threshold_fork_is_double_compare(oracle_mod, golden):
+    # iou == 0.7f (=0.69999998) must NOT be suppressed at thresh 0.7; iou == 0.3f must be
+    d = golden["nms_fork_dets"]
+    assert oracle_mod.clib.nms(d, 0.7) == [0, 1, 2, 3]
+    assert oracle_mod.clib.nms(d, 0.3) == [0, 2]
+
+
+def test_c_iou_matches_reference_golden(oracle_mod, golden):
+    b, q = golden["iou_boxes"], golden["iou_query"]
+    assert np.array_equal(oracle_mod.clib.bbox_overlaps(b, q), golden["iou_out"])
+    assert np.array_equal(oracle_mod.clib.bbox_overlaps(b, q, ui=True), golden["iou_ui_out"])
+
+
+def test_layers_bbox_transform_matches_reference_golden(oracle_mod, golden):
+    L = oracle_mod.layers
+    inv = L.bbox_transform_inv(golden["bt_boxes"], golden["bt_deltas"])
+    assert inv.dtype == np.float32
+    # np.exp is the only non-exact step; same numpy here as when the fixture was made
+    np.testing.assert_allclose(inv, golden["bt_inv"], rtol=1e-6, atol=1e-4)
+    clipped = L.clip_boxes(golden["bt_inv"].copy(), np.array([600, 800], np.float32))
+    assert np.array_equal(clipped, golden["bt_clip"])
+    t = L.bbox_transform(golden["bt_ex"], golden["bt_gt"]).astype(np.float32)
+    np.testing.assert_allclose(t, golden["bt_targets"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.skipif(not REFERENCE_PRESENT, reason="/root/reference only exists in the authoring container")
+def test_layers_vs_reference_module_by_path(oracle_mod):
+    spec = importlib.util.spec_from_file_location(
+        "ref_bt", "/root/reference/code/lib/fast_rcnn/bbox_transform.py")
+    bt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bt)
+    L = oracle_mod.layers
+    rng = np.random.default_rng(11)
+    boxes = syn.random_boxes(12, 500).astype(np.float64)
+    deltas = (rng.standard_normal((500, 4)) * 0.5).astype(np.float32)
+    assert np.array_equal(L.bbox_transform_inv(boxes, deltas), bt.bbox_transform_inv(boxes, deltas))
+    a = L.bbox_transform_inv(boxes, deltas)
+    assert np.array_equal(L.clip_boxes(a.copy(), (600, 800)), bt.clip_boxes(a.copy(), (600, 800)))
+    assert np.array_equal(L.bbox_transform(boxes, boxes[::-1]), bt.bbox_transform(boxes, boxes[::-1]))
+
+
+def test_ref_modules_vs_c_restatement(oracle_mod):
+    ref, clib = oracle_mod.ref, oracle_mod.clib
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (reference absent)")
+    for seed, n, kw in ((21, 700, {}), (22, 900, {"clustered": True})):
+        d = syn.dets(seed, n, **kw)
+        for t in (0.3, 0.5, 0.7):
+            assert ref.cpu_nms(d, t) == clib.nms(d, t)
+        assert ref.nms_new(d, 0.7) == clib.nms(d, 0.7, variant=1)
+    b = syn.random_boxes(23, 1500).astype(np.float64)
+    q = syn.random_boxes(24, 33).astype(np.float64)
+    assert np.array_equal(ref.bbox_overlaps(b, q), clib.bbox_overlaps(b, q))
+    assert np.array_equal(ref.bbox_overlaps_ui(b, q), clib.bbox_overlaps(b, q, ui=True))
+
+
+def test_nms_zero_union_raises(oracle_mod):
+    d = np.array([[5, 5, 4, 4, 0.9], [7, 7, 6, 6, 0.8]], np.float32)   # areas 0, no overlap
+    with pytest.raises(ZeroDivisionError):
+        oracle_mod.clib.nms(d, 0.5)
+    if oracle_mod.ref.available():
+        with pytest.raises(ZeroDivisionError):
+            oracle_mod.ref.cpu_nms(d, 0.5)
+
+
+# ---- RoI pooling: hand-derived expectations
+def _bins(clib, roi_h_cells, PH, mode):
+    """Which rows each ph pools, observed through argmax on a map whose value is its row."""
+    H, W, C = 80, 2, 1
+    bottom = np.zeros((1, H, W, C), np.float32)
+    bottom[0, :, :, 0] = np.arange(1, H + 1, dtype=np.float32)[:, None]   # increasing in h
+    roi = np.array([[0, 0, 0, 0, (roi_h_cells - 1) * 16]], np.float32)
+    top, arg = clib.roi_pool_fwd(bottom, roi, PH, 1, 1.0 / 16, bin_mode=mode)
+    # max of an increasing map = last row of the bin; recover first row from a decreasing map
+    bottom2 = bottom.copy()
+    bottom2[0, :, :, 0] = np.arange(H, 0, -1, dtype=np.float32)[:, None]
+    top2, arg2 = clib.roi_pool_fwd(bottom2, roi, PH, 1, 1.0 / 16, bin_mode=mode)
+    out = []
+    for ph in range(PH):
+        if arg[0, ph, 0, 0] < 0:
+            out.append(None)
+        else:
+            out.append((int(arg2[0, ph, 0, 0]) // (W * C), int(arg[0, ph, 0, 0]) // (W * C) + 1))
+    return out
+
+
+def test_roi_pool_bin_tables(oracle_mod):
+    clib = oracle_mod.clib
+    T, G = clib.CPU_TRUNC, clib.GPU_CEIL
+    assert _bins(clib, 10, 7, T) == [(0, 1), (1, 2), (2, 4), (4, 5), (5, 7), (7, 8), (8, 10)]
+    assert _bins(clib, 10, 7, G) == [(0, 2), (1, 3), (2, 5), (4, 6), (5, 8), (7, 9), (8, 10)]
+    assert _bins(clib, 3, 7, T) == [None, None, (0, 1), None, (1, 2), None, (2, 3)]
+    assert _bins(clib, 3, 7, G) == [(0, 1), (0, 1), (0, 2), (1, 2), (1, 3), (2, 3), (2, 3)]
+    assert _bins(clib, 14, 7, T) == [(2 * i, 2 * i + 2) for i in range(7)]
+    assert _bins(clib, 14, 7, G) == [(2 * i, 2 * i + 2) for i in range(7)]
+    # fp32 edge products: 7*fl(31/7) = 30.999998 -> CPU last edge 30, GPU 31
+    assert _bins(clib, 31, 7, T)[-1][1] == 30
+    assert _bins(clib, 31, 7, G)[-1][1] == 31
+    # 7*fl(57/7) = 57.000004 -> CPU 57, GPU 58 (one row past the RoI)
+    assert _bins(clib, 57, 7, T)[-1][1] == 57
+    assert _bins(clib, 57, 7, G)[-1][1] == 58
+
+
+def test_roi_pool_rounding_and_ties(oracle_mod):
+    clib = oracle_mod.clib
+    # round() is half away from zero: x=8 -> 0.5 -> 1 ; x=24 -> 1.5 -> 2 (np.round would give 0, 2)
+    bottom = np.zeros((1, 6, 6, 1), np.float32)
+    bottom[0, :, :, 0] = np.arange(36, dtype=np.float32).reshape(6, 6)
+    top, arg = clib.roi_pool_fwd(bottom, np.array([[0, 8, 8, 24, 24]], np.float32), 1, 1, 1 / 16.)
+    assert top[0, 0, 0, 0] == 14.0 and arg[0, 0, 0, 0] == 14     # cells 1..2 x 1..2 -> (2,2)
+    # ties: all-zero map -> first scanned cell wins, NOT -1
+    z = np.zeros((1, 6, 6, 2), np.float32)
+    top, arg = clib.roi_pool_fwd(z, np.array([[0, 16, 32, 64, 80]], np.float32), 1, 1, 1 / 16.)
+    assert top[0, 0, 0].tolist() == [0.0, 0.0]
+    assert arg[0, 0, 0].tolist() == [(2 * 6 + 1) * 2, (2 * 6 + 1) * 2 + 1]
+    # values <= -FLT_MAX never win: (-FLT_MAX, -1)
+    m = np.full((1, 2, 2, 1), -np.inf, np.float32)
+    top, arg = clib.roi_pool_fwd(m, np.array([[0, 0, 0, 31, 31]], np.float32), 1, 1, 1 / 16.)
+    assert top[0, 0, 0, 0] == -np.finfo(np.float32).max and arg[0, 0, 0, 0] == -1
+
+
+def test_roi_pool_bwd_literal_equals_fast(oracle_mod):
+    clib = oracle_mod.clib
+    rng = np.random.default_rng(31)
+    B, H, W, C, PH, PW = 2, 12, 14, 8, 7, 7
+    bottom = syn.feature_map(32, B, H, W, C)
+    rois = np.concatenate([syn.rois_for_pool(33, 40, B, im_w=W * 16, im_h=H * 16),
+                           syn.adversarial_rois(B, W, H)])
+    for mode in (clib.CPU_TRUNC, clib.GPU_CEIL):
+        top, arg = clib.roi_pool_fwd(bottom, rois, PH, PW, 1 / 16., bin_mode=mode)
+        g = rng.standard_normal(top.shape).astype(np.float32)
+        a = clib.roi_pool_bwd(g, arg, rois, bottom.shape, 1 / 16., literal=True)
+        b = clib.roi_pool_bwd(g, arg, rois, bottom.shape, 1 / 16., literal=False)
+        assert np.array_equal(a, b)
+        # scatter-through-argmax equals the gather except for malformed RoIs
+        wellformed = (rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2])
+        ref = np.zeros((B, H * W * C), np.float64)
+        for r in np.where(wellformed)[0]:
+            bi = int(rois[r, 0])
+            idx = arg[r].reshape(-1)
+            ok = idx >= 0
+            # GPU_CEIL can pool one row past the RoI (fl edge products); the gather's in-RoI
+            # test drops those, so only compare CPU_TRUNC against the plain scatter
+            np.add.at(ref[bi], idx[ok], g[r].reshape(-1)[ok].astype(np.float64))
+        if mode == clib.CPU_TRUNC:
+            np.testing.assert_allclose(a.reshape(B, -1), ref, rtol=1e-5, atol=1e-5)
+    # malformed RoIs: forward pools one cell, backward contributes nothing
+    bad = np.array([[0, 100, 40, 50, 120]], np.float32)   # x2 < x1, inside the 12x14 map
+    top, arg = clib.roi_pool_fwd(bottom, bad, PH, PW, 1 / 16.)
+    assert (arg >= 0).any()
+    gz = clib.roi_pool_bwd(np.ones_like(top), arg, bad, bottom.shape, 1 / 16., literal=True)
+    assert not gz.any()
+
+
+def test_proposal_layer_restatement_properties(oracle_mod):
+    L = oracle_mod.layers
+    cls, reg, info = syn.rpn_outputs(41, 2, 10, 12, 9, im_h=160, im_w=192)
+    cfg = dict(L.TEST, RPN_PRE_NMS_TOP_N=300, RPN_POST_NMS_TOP_N=50)
+    blob, parts = L.proposal_layer(cls, reg, info, cfg=cfg, return_parts=True)
+    assert blob.dtype == np.float32 and blob.shape[1] == 5
+    for b, p in enumerate(parts):
+        rows = blob[blob[:, 0] == b]
+        assert len(rows) == len(p["anchor_idx"]) <= 50
+        assert np.all(np.diff(p["scores"]) < 0)                      # descending, unique
+        assert np.all(rows[:, 1] >= 0) and np.all(rows[:, 3] <= 191) and np.all(rows[:, 4] <= 159)
+        assert np.all(rows[:, 3] - rows[:, 1] + 1 >= 16) and np.all(rows[:, 4] - rows[:, 2] + 1 >= 16)
+        # clip is idempotent
+        d = p["decoded"].copy()
+        assert np.array_equal(L.clip_boxes(d.copy(), info[b, :2]), d)

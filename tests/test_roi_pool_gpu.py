@@ -1,0 +1,158 @@
+"""RoI pooling parity on the GPU, through the C ABI (ctypes) behind wssdl_bus_b200.ops.
+Forward out+argmax: bit-exact vs the CPU restatement of roi_pooling_op.cc (both bin modes).
+Backward: deterministic gather bit-exact; atomic scatter within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+from wssdl_bus_b200 import ops, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+# tolerance for the atomics-accumulated gradient (north star: 1e-5 relative)
+RTOL, ATOL = 1e-5, 1e-5
+
+
+def _fwd_both(oracle_mod, bottom, rois, PH, PW, scale, mode):
+    want_top, want_arg = oracle_mod.clib.roi_pool_fwd(bottom, rois, PH, PW, scale,
+                                                      bin_mode=0 if mode == "cpu" else 1)
+    top, arg = ops.roi_pool_forward(bottom, rois, PH, PW, scale, bin_mode=mode)
+    return want_top, want_arg, top.cpu().numpy(), arg.cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", ["cpu", "gpu"])
+def test_fwd_c1_shapes_bit_exact(oracle_mod, mode):
+    c = syn.C1
+    bottom = syn.feature_map(0, c["B"], c["H"], c["W"], c["C"])
+    rois = syn.rois_for_pool(1, 300)
+    wt, wa, t, a = _fwd_both(oracle_mod, bottom, rois, 7, 7, c["scale"], mode)
+    assert np.array_equal(t, wt) and np.array_equal(a, wa)
+
+
+@pytest.mark.parametrize("mode", ["cpu", "gpu"])
+def test_fwd_adversarial_rois_bit_exact(oracle_mod, mode):
+    B, H, W, C = 2, 38, 50, 64
+    bottom = syn.feature_map(2, B, H, W, C)
+    bottom[0, 3:9, 4:11] = -np.inf                     # cells that can never win
+    bottom[1, 0, 0, :] = np.nan                        # NaN never wins either
+    rois = np.concatenate([syn.adversarial_rois(B, W, H), syn.rois_for_pool(3, 64, B)])
+    for PH, PW in ((7, 7), (14, 14), (6, 6), (1, 1), (3, 5)):
+        wt, wa, t, a = _fwd_both(oracle_mod, bottom, rois, PH, PW, 1 / 16., mode)
+        assert np.array_equal(a, wa)
+        assert np.array_equal(t, wt, equal_nan=True)
+
+
+@pytest.mark.parametrize("C", [3, 5, 32, 100, 1024])
+def test_fwd_channel_counts_and_scalar_path(oracle_mod, C):
+    # C=3 is the reference's own smoke shape (roi_pooling_op_test.py: 32x100x100x3, scale 1/3)
+    B, H, W = 2, 20, 24
+    bottom = syn.feature_map(4, B, H, W, C)
+    rois = syn.rois_for_pool(5, 17, B, im_w=W * 3, im_h=H * 3)
+    wt, wa, t, a = _fwd_both(oracle_mod, bottom, rois, 6, 6, 1 / 3., "cpu")
+    assert np.array_equal(t, wt) and np.array_equal(a, wa)
+
+
+def test_fwd_misaligned_pointer_uses_scalar_kernel(oracle_mod):
+    B, H, W, C = 1, 10, 12, 8
+    bottom = syn.feature_map(6, B, H, W, C)
+    rois = syn.rois_for_pool(7, 9, B, im_w=W * 16, im_h=H * 16)
+    buf = torch.zeros(bottom.size + 1, dtype=torch.float32, device="cuda")
+    view = buf[1:].view(B, H, W, C)                    # 4-byte aligned only
+    view.copy_(torch.from_numpy(bottom))
+    top, arg = ops.roi_pool_forward(view, rois, 7, 7, 1 / 16.)
+    wt, wa = oracle_mod.clib.roi_pool_fwd(bottom, rois, 7, 7, 1 / 16.)
+    assert np.array_equal(top.cpu().numpy(), wt) and np.array_equal(arg.cpu().numpy(), wa)
+
+
+def test_fwd_empty_and_errors():
+    bottom = torch.zeros((1, 4, 4, 8), device="cuda")
+    top, arg = ops.roi_pool_forward(bottom, np.zeros((0, 5), np.float32), 7, 7, 1 / 16.)
+    assert top.shape == (0, 7, 7, 8) and arg.shape == (0, 7, 7, 8)
+    with pytest.raises(ValueError, match="4-dimensional"):
+        ops.roi_pool_forward(bottom[0], np.zeros((1, 5), np.float32), 7, 7, 1.0)
+    with pytest.raises(ValueError, match="2-dimensional"):
+        ops.roi_pool_forward(bottom, np.zeros((5,), np.float32), 7, 7, 1.0)
+    with pytest.raises(ValueError, match="pooled_height"):
+        ops.roi_pool_forward(bottom, np.zeros((1, 5), np.float32), -1, 7, 1.0)
+    # batch index outside [0,B): documented (0, -1) instead of the reference's OOB read
+    top, arg = ops.roi_pool_forward(bottom + 1, np.array([[3, 0, 0, 40, 40]], np.float32), 2, 2, 1 / 16.)
+    assert float(top.abs().sum()) == 0 and int((arg != -1).sum()) == 0
+
+
+@pytest.mark.parametrize("mode", ["cpu", "gpu"])
+def test_bwd_gather_bit_exact_and_atomic_close(oracle_mod, mode):
+    B, H, W, C, PH, PW = 2, 38, 50, 64, 7, 7
+    bottom = syn.feature_map(8, B, H, W, C)
+    rois = np.concatenate([syn.rois_for_pool(9, 128, B), syn.adversarial_rois(B, W, H)])
+    rng = np.random.default_rng(10)
+    top, arg = ops.roi_pool_forward(bottom, rois, PH, PW, 1 / 16., bin_mode=mode)
+    g = rng.standard_normal(tuple(top.shape)).astype(np.float32)
+    want = oracle_mod.clib.roi_pool_bwd(g, arg.cpu().numpy(), rois, bottom.shape, 1 / 16.)
+    det = ops.roi_pool_backward(bottom.shape, rois, arg, g, PH, PW, 1 / 16., deterministic=True)
+    assert np.array_equal(det.cpu().numpy(), want)
+    atm = ops.roi_pool_backward(bottom.shape, rois, arg, g, PH, PW, 1 / 16., deterministic=False)
+    np.testing.assert_allclose(atm.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+
+
+def test_bwd_arbitrary_argmax_equals_reference_gather(oracle_mod):
+    """The reference's gradient is a gather with in-RoI and feasible-bin tests; a scatter
+    must reproduce it even for argmax tensors the forward would never produce."""
+    B, H, W, C, PH, PW = 1, 12, 14, 8, 4, 4
+    rois = syn.rois_for_pool(11, 20, B, im_w=W * 16, im_h=H * 16)
+    rng = np.random.default_rng(12)
+    arg = rng.integers(-1, H * W * C, size=(20, PH, PW, C)).astype(np.int32)
+    g = rng.standard_normal(arg.shape).astype(np.float32)
+    want = oracle_mod.clib.roi_pool_bwd(g, arg, rois, (B, H, W, C), 1 / 16., literal=True)
+    for det in (True, False):
+        got = ops.roi_pool_backward((B, H, W, C), rois, arg, g, PH, PW, 1 / 16., deterministic=det)
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+
+
+def test_c2_train_shapes_fwd_bwd(oracle_mod):
+    c = syn.C2
+    bottom = syn.feature_map(13, 1, c["H"], c["W"], c["C"])
+    rois = syn.rois_for_pool(14, c["sampled"])
+    rng = np.random.default_rng(15)
+    x = torch.from_numpy(bottom).cuda().requires_grad_(True)
+    top, arg = ops.roi_pool(x, rois, 7, 7, c["scale"])
+    wt, wa = oracle_mod.clib.roi_pool_fwd(bottom, rois, 7, 7, c["scale"])
+    assert np.array_equal(top.detach().cpu().numpy(), wt) and np.array_equal(arg.cpu().numpy(), wa)
+    g = rng.standard_normal(wt.shape).astype(np.float32)
+    top.backward(torch.from_numpy(g).cuda())
+    want = oracle_mod.clib.roi_pool_bwd(g, wa, rois, bottom.shape, c["scale"])
+    np.testing.assert_allclose(x.grad.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+    # drop-in names
+    from wssdl_bus_b200.roi_pooling_layer import roi_pooling_op
+    gg = roi_pooling_op.roi_pool_grad(x.detach(), rois, arg, g, 7, 7, c["scale"], deterministic=True)
+    assert np.array_equal(gg.cpu().numpy(), want)
+
+
+def test_c3_resnet_shapes_properties(oracle_mod):
+    """C3 at full size (16x38x50x1024, 4800 RoIs, 14x14): oracle on a slice, size-independent
+    properties on the whole: argmax inside its bin's image, top == bottom[argmax], gradient
+    mass conservation."""
+    c = syn.C3
+    B, H, W, C = c["B"], c["H"], c["W"], c["C"]
+    bottom = syn.feature_map(16, B, H, W, C)
+    rois = syn.rois_for_pool(17, B * c["rois_per_image"], B)
+    x = torch.from_numpy(bottom).cuda()
+    top, arg = ops.roi_pool_forward(x, rois, 14, 14, c["scale"])
+    sl = slice(0, 64)
+    wt, wa = oracle_mod.clib.roi_pool_fwd(bottom, rois[sl], 14, 14, c["scale"])
+    assert np.array_equal(top[sl].cpu().numpy(), wt) and np.array_equal(arg[sl].cpu().numpy(), wa)
+    # top == bottom[b, argmax] wherever argmax >= 0, 0 elsewhere
+    bidx = torch.from_numpy(rois[:, 0]).cuda().long()
+    flat = x.reshape(B, -1)
+    a = arg.reshape(arg.shape[0], -1).long()
+    gathered = flat[bidx[:, None].expand_as(a), a.clamp(min=0)]
+    t = top.reshape(top.shape[0], -1)
+    assert bool(torch.all(torch.where(a >= 0, gathered, torch.zeros_like(t)) == t))
+    # channel of the argmax is the output channel
+    cc = torch.arange(C, device="cuda").repeat(14 * 14)[None].expand_as(a)
+    assert bool(torch.all((a % C == cc) | (a < 0)))
+    # backward: total gradient mass is conserved (all RoIs well formed here)
+    g = torch.ones_like(top)
+    gb = ops.roi_pool_backward((B, H, W, C), rois, arg, g, 14, 14, c["scale"])
+    assert abs(float(gb.double().sum()) - float((arg >= 0).sum())) < 1e-3 * float((arg >= 0).sum())
+    gd = ops.roi_pool_backward((B, H, W, C), rois, arg, g, 14, 14, c["scale"], deterministic=True)
+    np.testing.assert_allclose(gb.cpu().numpy(), gd.cpu().numpy(), rtol=RTOL, atol=ATOL)

@@ -1,0 +1,65 @@
+// Shared helpers for the sm_100a kernels behind include/wssdl_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "../../include/wssdl_b200.h"
+
+#define WSSDL_NUM_SMS 148  // B200: 2 dies x 74 SMs
+
+#define WSSDL_RETURN_IF_CUDA(expr)              \
+  do {                                          \
+    cudaError_t _e = (expr);                    \
+    if (_e != cudaSuccess) return (int)_e;      \
+  } while (0)
+
+// Launch errors surface here without synchronising the stream.
+#define WSSDL_CHECK_LAUNCH()                    \
+  do {                                          \
+    cudaError_t _e = cudaGetLastError();        \
+    if (_e != cudaSuccess) return (int)_e;      \
+  } while (0)
+
+static inline cudaStream_t to_cuda(wssdl_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// RoI geometry in feature-map cells, computed exactly as the reference does
+// (roi_pooling_op.cc:153-165): C round() = half away from zero, float products.
+struct RoiCells {
+  int batch;
+  int start_w, start_h, end_w, end_h;
+  float bin_h, bin_w;
+};
+
+__device__ __forceinline__ RoiCells roi_cells(const float* __restrict__ roi, float spatial_scale,
+                                              int pooled_h, int pooled_w) {
+  RoiCells g;
+  g.batch = (int)roi[0];
+  g.start_w = (int)roundf(__fmul_rn(roi[1], spatial_scale));
+  g.start_h = (int)roundf(__fmul_rn(roi[2], spatial_scale));
+  g.end_w = (int)roundf(__fmul_rn(roi[3], spatial_scale));
+  g.end_h = (int)roundf(__fmul_rn(roi[4], spatial_scale));
+  int roi_w = max(g.end_w - g.start_w + 1, 1);  // malformed RoIs become 1x1 (:160-161)
+  int roi_h = max(g.end_h - g.start_h + 1, 1);
+  g.bin_h = __fdiv_rn((float)roi_h, (float)pooled_h);
+  g.bin_w = __fdiv_rn((float)roi_w, (float)pooled_w);
+  return g;
+}
+
+// Bin edge before the RoI offset is added.  CPU_TRUNC: the reference casts the float
+// product to int before floor/ceil (roi_pooling_op.cc:167-170) so both edges truncate;
+// GPU_CEIL: floor / ceil of the float product (roi_pooling_op_gpu.cu.cc:51-58).
+template <int BIN_MODE>
+__device__ __forceinline__ int bin_lo(int p, float bin) {
+  float v = __fmul_rn((float)p, bin);
+  return BIN_MODE == WSSDL_BIN_CPU_TRUNC ? (int)v : (int)floorf(v);
+}
+template <int BIN_MODE>
+__device__ __forceinline__ int bin_hi(int p, float bin) {
+  float v = __fmul_rn((float)(p + 1), bin);
+  return BIN_MODE == WSSDL_BIN_CPU_TRUNC ? (int)v : (int)ceilf(v);
+}

@@ -1,0 +1,431 @@
+// Greedy NMS on the device for sm_100a: sort -> 64-bit bitmask over the upper triangle ->
+// on-device sweep.  Semantics: cpu_nms (nms/cpu_nms.pyx:17-68), utils.cython_nms.nms /
+// nms_new (utils/nms.pyx), gpu_nms/_nms (nms/nms_kernel.cu:34-144), py_cpu_nms.
+//
+// Stages (all on the caller's stream, scratch in the caller's workspace, no host round
+// trip -- the reference copies the N x N/64 mask to the host and sweeps there,
+// nms_kernel.cu:118-139):
+//   1. key build: 64-bit key = (~orderable(score) << 32) | ~index, so an ascending sort
+//      yields (score desc, index desc) = scores.argsort(kind='stable')[::-1];
+//   2. bitonic sort of the padded key array (shared-memory tiles of 4096 keys, global
+//      compare-exchange passes only for strides >= 4096);
+//   3. gather: sorted boxes as float4 + the fp32 area computed like numpy does
+//      (cpu_nms.pyx:24: one rounding per operation);
+//   4. mask: one thread per sorted row and 64-column block, column boxes staged in shared
+//      memory; only blocks on or above the diagonal are computed;
+//   5. sweep: one CTA; per 64-row block a single warp resolves the diagonal word set with a
+//      ballot-style fixed-point iteration (K <- alive & ~OR_{i in K} row_i, unique fixed
+//      point = the greedy solution because the dependency matrix is strictly upper
+//      triangular), then all threads OR the kept rows into the removal bitmap.
+//
+// IoU arithmetic mirrors the generated C of the reference (cpu_nms.c:2442-2495): every
+// operation is a single fp32 rounding (no FMA), IEEE division, and the threshold test is
+// done in the precision the chosen mode prescribes.
+#include <math.h>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int SORT_TILE = 4096;      // keys per shared-memory tile (32 KB)
+constexpr int SORT_THREADS = 1024;
+
+__device__ __forceinline__ unsigned orderable(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void nms_build_keys(const float* __restrict__ dets, int N, int stride, int npad,
+                               unsigned long long* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npad) return;
+  unsigned long long k = ~0ull;  // padding sorts last
+  if (i < N) {
+    const unsigned s = orderable(dets[(size_t)i * stride + 4]);
+    k = ((unsigned long long)(~s) << 32) | (unsigned)(~(unsigned)i);
+  }
+  keys[i] = k;
+}
+
+__device__ __forceinline__ void cmpxchg(unsigned long long& a, unsigned long long& b, bool up) {
+  if ((a > b) == up) { unsigned long long t = a; a = b; b = t; }
+}
+
+// Sort each SORT_TILE-key tile completely (bitonic); direction alternates per tile so the
+// tiles form bitonic sequences for the global merge stages.
+__global__ void __launch_bounds__(SORT_THREADS)
+bitonic_tile_sort(unsigned long long* __restrict__ keys) {
+  __shared__ unsigned long long s[SORT_TILE];
+  const size_t base = (size_t)blockIdx.x * SORT_TILE;
+  for (int i = threadIdx.x; i < SORT_TILE; i += SORT_THREADS) s[i] = keys[base + i];
+  __syncthreads();
+  for (int k = 2; k <= SORT_TILE; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < SORT_TILE / 2; t += SORT_THREADS) {
+        const int i = 2 * t - (t & (j - 1));  // lower index of the pair with stride j
+        const size_t gi = base + i;
+        const bool up = ((gi & (size_t)k) == 0);
+        cmpxchg(s[i], s[i + j], up);
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < SORT_TILE; i += SORT_THREADS) keys[base + i] = s[i];
+}
+
+// One global compare-exchange pass: stage size k, stride j >= SORT_TILE.
+__global__ void bitonic_global_step(unsigned long long* __restrict__ keys, int npad, int k,
+                                    int j) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npad / 2) return;
+  const int i = 2 * t - (t & (j - 1));
+  const bool up = ((i & k) == 0);
+  unsigned long long a = keys[i], b = keys[i + j];
+  if ((a > b) == up) { keys[i] = b; keys[i + j] = a; }
+}
+
+// Finish stage k inside a tile: all strides j < SORT_TILE.
+__global__ void __launch_bounds__(SORT_THREADS)
+bitonic_tile_merge(unsigned long long* __restrict__ keys, int k) {
+  __shared__ unsigned long long s[SORT_TILE];
+  const size_t base = (size_t)blockIdx.x * SORT_TILE;
+  for (int i = threadIdx.x; i < SORT_TILE; i += SORT_THREADS) s[i] = keys[base + i];
+  __syncthreads();
+  const bool up = ((base & (size_t)k) == 0);
+  for (int j = SORT_TILE >> 1; j > 0; j >>= 1) {
+    for (int t = threadIdx.x; t < SORT_TILE / 2; t += SORT_THREADS) {
+      const int i = 2 * t - (t & (j - 1));
+      cmpxchg(s[i], s[i + j], up);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < SORT_TILE; i += SORT_THREADS) keys[base + i] = s[i];
+}
+
+// sorted position p -> original index, box (float4) and numpy-style fp32 area
+__global__ void nms_gather(const float* __restrict__ dets, int N, int stride,
+                           const unsigned long long* __restrict__ keys, int presorted,
+                           int* __restrict__ order, float4* __restrict__ boxes,
+                           float* __restrict__ areas) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int i = presorted ? p : (int)(~(unsigned)(keys[p] & 0xffffffffull));
+  const float* d = dets + (size_t)i * stride;
+  const float x1 = d[0], y1 = d[1], x2 = d[2], y2 = d[3];
+  order[p] = i;
+  boxes[p] = make_float4(x1, y1, x2, y2);
+  // (x2 - x1 + 1) * (y2 - y1 + 1), each op rounded to fp32 (cpu_nms.pyx:24)
+  areas[p] = __fmul_rn(__fadd_rn(__fsub_rn(x2, x1), 1.0f), __fadd_rn(__fsub_rn(y2, y1), 1.0f));
+}
+
+struct Thresh {
+  float ge;       // mode GE_F64: smallest float whose double value is >= thresh
+  float gt;       // mode GT_F32: (float)thresh, test is '>'
+  int use_gt;
+  int contain;    // nms_new's extra containment tests
+};
+
+// max/min exactly as cpu_nms.pyx:11-15 (NaN-asymmetric like the reference)
+__device__ __forceinline__ float rmax(float a, float b) { return a >= b ? a : b; }
+__device__ __forceinline__ float rmin(float a, float b) { return a <= b ? a : b; }
+
+// true iff box j (lower score) is suppressed by box i (higher score); *zero is set when
+// the union is exactly zero (the reference raises ZeroDivisionError when it visits such a
+// pair, cpu_nms.c:2480-2483).
+__device__ __forceinline__ bool suppresses(const float4 bi, float ai, const float4 bj, float aj,
+                                           const Thresh th, bool* zero) {
+  const float xx1 = rmax(bi.x, bj.x), yy1 = rmax(bi.y, bj.y);
+  const float xx2 = rmin(bi.z, bj.z), yy2 = rmin(bi.w, bj.w);
+  const float w = rmax(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+  const float h = rmax(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+  const float inter = __fmul_rn(w, h);
+  const float den = __fsub_rn(__fadd_rn(ai, aj), inter);
+  if (den == 0.0f) *zero = true;
+  const float ovr = __fdiv_rn(inter, den);
+  bool s = th.use_gt ? (ovr > th.gt) : (ovr >= th.ge);
+  if (th.contain) {
+    // nms.pyx:117-120: float division, compared against the double 0.95: x > 0.95 for a float x
+    // is x > 0.949999988f (the largest float below 0.95), i.e. x >= 0.95000005f
+    const float c95 = 0.949999988079071044921875f;
+    if (ai == 0.0f || aj == 0.0f) *zero = true;   // the reference raises there as well
+    s = s || (__fdiv_rn(inter, ai) > c95) || (__fdiv_rn(inter, aj) > c95);
+  }
+  return s;
+}
+
+constexpr int MASK_ROWS = 256;  // rows (threads) per CTA of the mask kernel
+
+// mask[row * col_blocks + cb] bit c = sorted box row suppresses sorted box 64*cb+c (c > row)
+__global__ void __launch_bounds__(MASK_ROWS)
+nms_mask_kernel(const float4* __restrict__ boxes, const float* __restrict__ areas, int N,
+                int col_blocks, Thresh th, unsigned long long* __restrict__ mask,
+                int* __restrict__ status) {
+  const int cb = blockIdx.x;
+  const int row0 = blockIdx.y * MASK_ROWS;
+  if (64 * cb + 63 <= row0) return;  // every column <= every row: below the diagonal
+  __shared__ float4 s_box[64];
+  __shared__ float s_area[64];
+  const int ncol = min(64, N - 64 * cb);
+  if (threadIdx.x < ncol) {
+    s_box[threadIdx.x] = boxes[64 * cb + threadIdx.x];
+    s_area[threadIdx.x] = areas[64 * cb + threadIdx.x];
+  }
+  __syncthreads();
+  const int row = row0 + threadIdx.x;
+  if (row >= N || (row >> 6) > cb) return;
+  const float4 bi = boxes[row];
+  const float ai = areas[row];
+  const int start = ((row >> 6) == cb) ? (row & 63) + 1 : 0;
+  unsigned long long bits = 0;
+  bool zero = false;
+  for (int c = start; c < ncol; ++c) {
+    if (suppresses(bi, ai, s_box[c], s_area[c], th, &zero)) bits |= 1ull << c;
+  }
+  mask[(size_t)row * col_blocks + cb] = bits;
+  if (zero && status != nullptr) status[0] = 1;
+}
+
+constexpr int SWEEP_THREADS = 1024;
+
+// Single-CTA sweep.  remv (one bit per sorted box) lives in shared memory.
+__global__ void __launch_bounds__(SWEEP_THREADS)
+nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blocks,
+                 const int* __restrict__ order, int max_keep, int* __restrict__ keep,
+                 int* __restrict__ num_keep) {
+  extern __shared__ unsigned long long remv[];   // col_blocks words
+  __shared__ unsigned long long s_kept;
+  __shared__ int s_count;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < col_blocks; i += SWEEP_THREADS) remv[i] = 0;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  const int limit = max_keep > 0 ? min(max_keep, N) : N;
+
+  for (int b = 0; b < col_blocks; ++b) {
+    if (tid < 32) {
+      // diagonal words of rows 64b+lane and 64b+32+lane
+      const int r0 = 64 * b + lane, r1 = r0 + 32;
+      const unsigned long long d0 = r0 < N ? mask[(size_t)r0 * col_blocks + b] : 0ull;
+      const unsigned long long d1 = r1 < N ? mask[(size_t)r1 * col_blocks + b] : 0ull;
+      const int nrow = min(64, N - 64 * b);
+      const unsigned long long valid = nrow == 64 ? ~0ull : ((1ull << nrow) - 1ull);
+      const unsigned long long alive = ~remv[b] & valid;
+      unsigned long long K = alive;
+      for (int it = 0; it < 64; ++it) {
+        unsigned long long mine = 0;
+        if ((K >> lane) & 1ull) mine |= d0;
+        if ((K >> (lane + 32)) & 1ull) mine |= d1;
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mine);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(mine >> 32));
+        const unsigned long long Knew = alive & ~(((unsigned long long)hi << 32) | lo);
+        if (Knew == K) break;
+        K = Knew;
+      }
+      // truncate to the first (limit - count) kept boxes of this block
+      int count = s_count;
+      int take = __popcll(K);
+      if (count + take > limit) {
+        int over = count + take - limit;
+        while (over-- > 0) K &= ~(1ull << (63 - __clzll(K)));
+        take = limit - count;
+      }
+      // write kept indices in order
+      if ((K >> lane) & 1ull)
+        keep[count + __popcll(K & ((1ull << lane) - 1ull))] = order[r0];
+      if ((K >> (lane + 32)) & 1ull)
+        keep[count + __popcll(K & ((1ull << (lane + 32)) - 1ull))] = order[r1];
+      if (lane == 0) { s_kept = K; s_count = count + take; }
+    }
+    __syncthreads();
+    const unsigned long long K = s_kept;
+    if (s_count >= limit) break;
+    // OR the kept rows of this block into the removal bitmap for later column blocks
+    for (int j = b + 1 + tid; j < col_blocks; j += SWEEP_THREADS) {
+      unsigned long long acc = 0;
+      unsigned long long rem = K;
+      while (rem) {
+        const int i = __ffsll((long long)rem) - 1;
+        rem &= rem - 1;
+        acc |= mask[(size_t)(64 * b + i) * col_blocks + j];
+      }
+      remv[j] |= acc;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *num_keep = s_count;
+}
+
+struct Layout {
+  int npad;
+  size_t keys, order, boxes, areas, mask, total;
+};
+
+Layout layout_for(int N) {
+  Layout L;
+  int npad = SORT_TILE;
+  while (npad < N) npad <<= 1;
+  L.npad = npad;
+  const size_t cb = (size_t)(N + 63) / 64;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  L.keys = take(sizeof(unsigned long long) * (size_t)npad);
+  L.order = take(sizeof(int) * (size_t)N);
+  L.boxes = take(sizeof(float4) * (size_t)N);
+  L.areas = take(sizeof(float) * (size_t)N);
+  L.mask = take(sizeof(unsigned long long) * (size_t)N * cb);
+  L.total = off;
+  return L;
+}
+
+Thresh make_thresh(double thresh, int mode) {
+  Thresh t;
+  t.use_gt = (mode & 3) == WSSDL_NMS_GT_F32;
+  t.contain = (mode & WSSDL_NMS_CONTAIN) ? 1 : 0;
+  t.gt = (float)thresh;
+  // smallest float f with (double)f >= thresh
+  float f = (float)thresh;
+  if ((double)f < thresh) f = nextafterf(f, INFINITY);
+  t.ge = f;
+  return t;
+}
+
+int run_nms(const float* dets, int N, int stride, double thresh, int mode, int max_keep,
+            int presorted, int* keep, int* num_keep, int* status, void* workspace,
+            size_t workspace_bytes, cudaStream_t s) {
+  if (N < 0 || stride < 5 || !num_keep) return WSSDL_EINVAL;
+  if ((mode & ~(3 | WSSDL_NMS_CONTAIN)) != 0 || (mode & 3) > 1) return WSSDL_EINVAL;
+  if (status) WSSDL_RETURN_IF_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int), s));
+  if (N == 0) {
+    WSSDL_RETURN_IF_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int), s));
+    return WSSDL_OK;
+  }
+  if (!dets || !keep || !workspace) return WSSDL_EINVAL;
+  if (N > (1 << 20)) return WSSDL_ELIMIT;   // sweep bitmap and int indexing
+  const Layout L = layout_for(N);
+  if (workspace_bytes < L.total) return WSSDL_EWORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return WSSDL_EALIGN;
+  char* ws = static_cast<char*>(workspace);
+  auto* keys = reinterpret_cast<unsigned long long*>(ws + L.keys);
+  int* order = reinterpret_cast<int*>(ws + L.order);
+  float4* boxes = reinterpret_cast<float4*>(ws + L.boxes);
+  float* areas = reinterpret_cast<float*>(ws + L.areas);
+  auto* mask = reinterpret_cast<unsigned long long*>(ws + L.mask);
+  const int col_blocks = (N + 63) / 64;
+
+  if (!presorted) {
+    nms_build_keys<<<ceil_div(L.npad, 256), 256, 0, s>>>(dets, N, stride, L.npad, keys);
+    const int tiles = L.npad / SORT_TILE;
+    bitonic_tile_sort<<<tiles, SORT_THREADS, 0, s>>>(keys);
+    for (int k = 2 * SORT_TILE; k <= L.npad; k <<= 1) {
+      for (int j = k >> 1; j >= SORT_TILE; j >>= 1)
+        bitonic_global_step<<<ceil_div(L.npad / 2, 256), 256, 0, s>>>(keys, L.npad, k, j);
+      bitonic_tile_merge<<<tiles, SORT_THREADS, 0, s>>>(keys, k);
+    }
+  }
+  nms_gather<<<ceil_div(N, 256), 256, 0, s>>>(dets, N, stride, keys, presorted, order, boxes,
+                                             areas);
+  const Thresh th = make_thresh(thresh, mode);
+  dim3 mgrid((unsigned)col_blocks, (unsigned)ceil_div(N, MASK_ROWS));
+  nms_mask_kernel<<<mgrid, MASK_ROWS, 0, s>>>(boxes, areas, N, col_blocks, th, mask, status);
+  nms_sweep_kernel<<<1, SWEEP_THREADS, sizeof(unsigned long long) * (size_t)col_blocks, s>>>(
+      mask, N, col_blocks, order, max_keep, keep, num_keep);
+  WSSDL_CHECK_LAUNCH();
+  return WSSDL_OK;
+}
+
+// Grow-only device scratch for the *_host entry points (one per process, mutex-guarded).
+std::mutex g_host_mu;
+void* g_host_buf = nullptr;
+size_t g_host_cap = 0;
+int g_host_dev = -1;
+
+int host_scratch(size_t bytes, int device, void** out) {
+  if (g_host_buf && (g_host_cap < bytes || g_host_dev != device)) {
+    cudaFree(g_host_buf);
+    g_host_buf = nullptr;
+    g_host_cap = 0;
+  }
+  if (!g_host_buf) {
+    WSSDL_RETURN_IF_CUDA(cudaMalloc(&g_host_buf, bytes));
+    g_host_cap = bytes;
+    g_host_dev = device;
+  }
+  *out = g_host_buf;
+  return WSSDL_OK;
+}
+
+int nms_host_common(int* keep_out, int* num_out, const float* dets_host, int N, int stride,
+                    double thresh, int mode, int max_keep, int presorted, int device_id) {
+  if (!num_out) return WSSDL_EINVAL;
+  *num_out = 0;
+  if (N == 0) return WSSDL_OK;
+  if (N < 0 || !keep_out || !dets_host || stride < 4) return WSSDL_EINVAL;
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  WSSDL_RETURN_IF_CUDA(cudaSetDevice(device_id));
+  const size_t ws_bytes = layout_for(N).total;
+  const size_t dets_bytes = ((sizeof(float) * (size_t)N * 5) + 255) & ~(size_t)255;
+  const size_t keep_bytes = ((sizeof(int) * (size_t)N) + 255) & ~(size_t)255;
+  void* buf = nullptr;
+  int rc = host_scratch(ws_bytes + dets_bytes + keep_bytes + 256, device_id, &buf);
+  if (rc != WSSDL_OK) return rc;
+  char* p = static_cast<char*>(buf);
+  float* d_dets = reinterpret_cast<float*>(p + ws_bytes);
+  int* d_keep = reinterpret_cast<int*>(p + ws_bytes + dets_bytes);
+  int* d_misc = reinterpret_cast<int*>(p + ws_bytes + dets_bytes + keep_bytes);  // num, status[2]
+  cudaStream_t s = 0;
+  if (stride == 5) {
+    WSSDL_RETURN_IF_CUDA(cudaMemcpyAsync(d_dets, dets_host, sizeof(float) * (size_t)N * 5,
+                                         cudaMemcpyHostToDevice, s));
+  } else {
+    // boxes_dim != 5: copy the first min(stride,5) columns of every row, pad the score with 0
+    WSSDL_RETURN_IF_CUDA(cudaMemsetAsync(d_dets, 0, sizeof(float) * (size_t)N * 5, s));
+    WSSDL_RETURN_IF_CUDA(cudaMemcpy2DAsync(d_dets, 5 * sizeof(float), dets_host,
+                                           (size_t)stride * sizeof(float),
+                                           (size_t)(stride < 5 ? stride : 5) * sizeof(float),
+                                           (size_t)N, cudaMemcpyHostToDevice, s));
+  }
+  rc = run_nms(d_dets, N, 5, thresh, mode, max_keep, presorted, d_keep, d_misc, d_misc + 1, buf,
+               ws_bytes, s);
+  if (rc != WSSDL_OK) return rc;
+  int misc[3];
+  WSSDL_RETURN_IF_CUDA(cudaMemcpyAsync(misc, d_misc, sizeof(misc), cudaMemcpyDeviceToHost, s));
+  WSSDL_RETURN_IF_CUDA(cudaStreamSynchronize(s));
+  if (misc[0] > 0)
+    WSSDL_RETURN_IF_CUDA(cudaMemcpy(keep_out, d_keep, sizeof(int) * (size_t)misc[0],
+                                    cudaMemcpyDeviceToHost));
+  *num_out = misc[0];
+  return misc[1] ? WSSDL_EZERODIV : WSSDL_OK;
+}
+
+}  // namespace
+
+extern "C" size_t wssdl_nms_workspace_bytes(int N) {
+  if (N <= 0) return 256;
+  return layout_for(N).total;
+}
+
+extern "C" int wssdl_nms(const float* dets, int N, int dets_stride, double thresh, int mode,
+                         int max_keep, int* keep, int* num_keep, int* status, void* workspace,
+                         size_t workspace_bytes, wssdl_stream_t stream) {
+  return run_nms(dets, N, dets_stride, thresh, mode, max_keep, /*presorted=*/0, keep, num_keep,
+                 status, workspace, workspace_bytes, to_cuda(stream));
+}
+
+extern "C" int wssdl_gpu_nms_host(int* keep_out, int* num_out, const float* boxes_host,
+                                  int boxes_num, int boxes_dim, float nms_overlap_thresh,
+                                  int device_id) {
+  // same contract as `_nms` (nms_kernel.cu:91): input sorted by the caller, '>' test in
+  // fp32, keep_out holds positions in the sorted array.
+  return nms_host_common(keep_out, num_out, boxes_host, boxes_num, boxes_dim,
+                         (double)nms_overlap_thresh, WSSDL_NMS_GT_F32, 0, /*presorted=*/1,
+                         device_id);
+}
+
+extern "C" int wssdl_nms_host(int* keep_out, int* num_out, const float* dets_host, int N,
+                              int dets_stride, double thresh, int mode, int max_keep,
+                              int device_id) {
+  if (dets_stride < 5) return WSSDL_EINVAL;
+  return nms_host_common(keep_out, num_out, dets_host, N, dets_stride, thresh, mode, max_keep,
+                         /*presorted=*/0, device_id);
+}

@@ -1,0 +1,459 @@
+// Fused RPN proposal layer for sm_100a: one CTA per image, everything between the RPN
+// head outputs and the RoI blob happens in shared memory.
+//
+// Semantics: proposal_layer (rpn_msr/proposal_layer_tf_bus.py:19-148) =
+//   anchors (generate_anchors.py + shifts :55-71) -> bbox_transform_inv
+//   (fast_rcnn/bbox_transform.py:30-61) -> clip_boxes (:63-77) -> _filter_boxes
+//   (proposal_layer_tf_bus.py:151-156) -> argsort desc + pre-NMS top-N (:129-133) ->
+//   cpu_nms (nms/cpu_nms.pyx:17-68) -> post-NMS top-N (:139-146) -> (R,5) blob.
+//
+// Phases of the kernel (1024 threads, one image):
+//   1. decode+clip+filter every anchor; keep only a 32-bit orderable score key per anchor
+//      in shared memory (0 = filtered out).  Boxes are NOT stored: they are a pure
+//      function of (anchor index, 4 deltas) and are recomputed bit-identically when needed.
+//   2. radix select (4 x 8-bit histogram passes over the shared keys) of the K-th largest
+//      key, K = min(pre_nms_topN, #valid); ties at the threshold are resolved by a second
+//      select on the anchor index so exactly K survive (score desc, index desc).
+//   3. compaction of the K survivors as 64-bit (~key, ~index) words + in-shared bitonic
+//      sort => the reference's descending-score order.
+//   4. NMS driven by the keep list instead of an N x N mask: post_nms_topN is small
+//      (300 / 2000) so a candidate only has to be tested against boxes ALREADY KEPT
+//      (<= post_nms_topN) and the loop stops as soon as the list is full.  Candidates are
+//      taken in chunks of 256 in score order:
+//        A. 4 threads per candidate scan the kept list (early exit on first hit);
+//        B. for the survivors, 64-bit column masks of the chunk's own upper triangle;
+//        C. one warp resolves the chunk with ballots: per 32-candidate sub-block a
+//           fixed-point iteration K <- alive & ~any(col & K), whose unique fixed point is
+//           the greedy answer (dependencies only point to earlier candidates);
+//        D. newly kept boxes are appended to the list and written to the output blob.
+//
+// IoU arithmetic = cpu_nms's fp32 sequence with the double-threshold compare
+// (cpu_nms.c:2442-2495), one rounding per operation.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int PT = 1024;         // threads per CTA
+constexpr int CHUNK = 256;       // NMS candidates per round
+constexpr int MAX_ANCHORS = 32; // base anchors per cell
+
+struct PropParams {
+  const float* cls_prob;
+  const float* bbox_pred;
+  const float* im_info;
+  int info_stride;
+  int H, W, A, NA;
+  int feat_stride;
+  int pre_nms_topN, post_nms_topN;
+  int kpad;                      // power of two >= min(pre_nms_topN, NA)
+  float thr_ge;                  // smallest float whose double value is >= nms_thresh
+  float min_size;
+  float* rois;
+  float* scores;
+  int* anchor_idx;
+  int* counts;
+  float* decoded;                // optional [B,NA,4]
+  float base[MAX_ANCHORS * 4];   // base anchors, by value (constant bank, no extra copy)
+};
+
+__device__ __forceinline__ unsigned orderable_key(float f) {
+  unsigned u = __float_as_uint(f);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return u == 0u ? 1u : u;       // 0 is reserved for "filtered out"
+}
+__device__ __forceinline__ float key_to_float(unsigned k) {
+  unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+
+__device__ __forceinline__ float clip_np(float v, float hi) {
+  float t = (v != v) ? v : (v < hi ? v : hi);     // np.minimum
+  return (t != t) ? t : (t > 0.f ? t : 0.f);      // np.maximum(., 0)
+}
+
+// decode + clip anchor `a` (row order (h, w, anchor)) of image `img`
+__device__ __forceinline__ float4 decode_anchor(const PropParams& p, int img, int a, float im_h,
+                                                float im_w) {
+  const int cell = a / p.A;
+  const int an = a - cell * p.A;
+  const int y = cell / p.W;
+  const int x = cell - y * p.W;
+  const float sx = (float)(x * p.feat_stride), sy = (float)(y * p.feat_stride);
+  const float ax1 = p.base[4 * an] + sx, ay1 = p.base[4 * an + 1] + sy;
+  const float ax2 = p.base[4 * an + 2] + sx, ay2 = p.base[4 * an + 3] + sy;
+  const float* d = p.bbox_pred + ((size_t)img * p.H * p.W + cell) * (4 * p.A) + 4 * an;
+  const float dx = __ldg(d), dy = __ldg(d + 1), dw = __ldg(d + 2), dh = __ldg(d + 3);
+  const float w = __fadd_rn(__fsub_rn(ax2, ax1), 1.0f);
+  const float h = __fadd_rn(__fsub_rn(ay2, ay1), 1.0f);
+  const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, w));
+  const float cy = __fadd_rn(ay1, __fmul_rn(0.5f, h));
+  const float pcx = __fadd_rn(__fmul_rn(dx, w), cx);
+  const float pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+  const float pw = __fmul_rn(exp_cr(dw), w);
+  const float ph = __fmul_rn(exp_cr(dh), h);
+  float4 b;
+  b.x = clip_np(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), __fsub_rn(im_w, 1.0f));
+  b.y = clip_np(__fsub_rn(pcy, __fmul_rn(0.5f, ph)), __fsub_rn(im_h, 1.0f));
+  b.z = clip_np(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), __fsub_rn(im_w, 1.0f));
+  b.w = clip_np(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), __fsub_rn(im_h, 1.0f));
+  return b;
+}
+
+__device__ __forceinline__ float rmax(float a, float b) { return a >= b ? a : b; }
+__device__ __forceinline__ float rmin(float a, float b) { return a <= b ? a : b; }
+
+__device__ __forceinline__ bool iou_ge(const float4 bi, float ai, const float4 bj, float aj,
+                                       float thr_ge) {
+  const float xx1 = rmax(bi.x, bj.x), yy1 = rmax(bi.y, bj.y);
+  const float xx2 = rmin(bi.z, bj.z), yy2 = rmin(bi.w, bj.w);
+  const float w = rmax(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+  const float h = rmax(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+  const float inter = __fmul_rn(w, h);
+  const float den = __fsub_rn(__fadd_rn(ai, aj), inter);
+  return __fdiv_rn(inter, den) >= thr_ge;
+}
+
+// K-th largest (1-based) among n keys in shared memory, considering only keys accepted by
+// `accept`; returns the threshold key T and, through *n_greater, how many accepted keys
+// are strictly greater than T.  4 passes of 8 bits, MSB first.  All threads must call.
+template <typename KeyFn>
+__device__ unsigned radix_select(KeyFn key_at, int n, int K, unsigned* s_hist /*256*/,
+                                 unsigned* s_bcast /*4*/, int* n_greater) {
+  unsigned prefix = 0, prefix_mask = 0;
+  int remaining = K;     // rank still to be found inside the current prefix bucket
+  int greater = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += PT) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += PT) {
+      const unsigned k = key_at(i);
+      if (k != 0u && (k & prefix_mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // scan the 256 bins from the top; lane l owns bins 255-8l .. 248-8l
+      const int lane = threadIdx.x;
+      unsigned c[8];
+      unsigned sum = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { c[q] = s_hist[255 - (8 * lane + q)]; sum += c[q]; }
+      unsigned incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      unsigned before = incl - sum;   // keys in bins above this lane's bins
+      if (before < (unsigned)remaining && (unsigned)remaining <= incl) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (before < (unsigned)remaining && (unsigned)remaining <= before + c[q]) {
+            s_bcast[0] = 255 - (8 * lane + q);   // digit of the K-th key
+            s_bcast[1] = before;                 // accepted keys above that digit
+          }
+          before += c[q];
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned digit = s_bcast[0];
+    greater += (int)s_bcast[1];
+    remaining -= (int)s_bcast[1];
+    prefix |= digit << shift;
+    prefix_mask |= 255u << shift;
+    __syncthreads();
+  }
+  *n_greater = greater;
+  return prefix;
+}
+
+__global__ void __launch_bounds__(PT, 1)
+proposals_kernel(const PropParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: sort buffer (kpad u64) | keys (NA u32) | per-chunk NMS state | kept list
+  unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem_raw);
+  unsigned* s_keys = reinterpret_cast<unsigned*>(s_sort + p.kpad);
+  const int na_pad = (p.NA + 3) & ~3;
+  float4* s_cbox = reinterpret_cast<float4*>(s_keys + na_pad);                 // [CHUNK]
+  unsigned long long* s_col = reinterpret_cast<unsigned long long*>(s_cbox + CHUNK);  // [CHUNK][4]
+  float* s_carea = reinterpret_cast<float*>(s_col + CHUNK * 4);                // [CHUNK]
+  int* s_cidx = reinterpret_cast<int*>(s_carea + CHUNK);                       // [CHUNK]
+  unsigned* s_alive = reinterpret_cast<unsigned*>(s_cidx + CHUNK);             // [CHUNK/32]
+  unsigned* s_kmask = s_alive + CHUNK / 32;                                    // [CHUNK/32]
+  unsigned* s_hist = s_kmask + CHUNK / 32;                                     // [256]
+  unsigned* s_bcast = s_hist + 256;                                            // [4]
+  int* s_cnt = reinterpret_cast<int*>(s_bcast + 4);                            // [4]
+  float4* s_kbox = reinterpret_cast<float4*>(s_cnt + 4);                       // [post]
+  float* s_karea = reinterpret_cast<float*>(s_kbox + p.post_nms_topN);         // [post]
+
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* info = p.im_info + (size_t)img * p.info_stride;
+  const float im_h = info[0], im_w = info[1];
+  const float min_size = __fmul_rn(p.min_size, info[2]);    // :123, fp32 product
+  const int post = p.post_nms_topN;
+
+  // ---- phase 1: decode, clip, filter -> keys
+  if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+  __syncthreads();
+  int my_valid = 0;
+  for (int a = tid; a < p.NA; a += PT) {
+    const float4 b = decode_anchor(p, img, a, im_h, im_w);
+    if (p.decoded) reinterpret_cast<float4*>(p.decoded)[(size_t)img * p.NA + a] = b;
+    const float ws = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f);
+    const float hs = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
+    const bool ok = (ws >= min_size) && (hs >= min_size);
+    const int cell = a / p.A;
+    const int an = a - cell * p.A;
+    const float sc = __ldg(p.cls_prob + ((size_t)img * p.H * p.W + cell) * (2 * p.A) + p.A + an);
+    s_keys[a] = ok ? orderable_key(sc) : 0u;
+    my_valid += ok ? 1 : 0;
+  }
+  my_valid = __reduce_add_sync(0xffffffffu, my_valid);
+  if (lane == 0 && my_valid) atomicAdd(&s_cnt[0], my_valid);
+  __syncthreads();
+  const int n_valid = s_cnt[0];
+  const int K = min(p.pre_nms_topN, n_valid);
+
+  // ---- phase 2: threshold key (and threshold index among ties)
+  unsigned T = 0, T2 = 0;
+  if (K < n_valid) {
+    int n_gt = 0;
+    T = radix_select([&](int i) { return s_keys[i]; }, p.NA, K, s_hist, s_bcast, &n_gt);
+    const int need_eq = K - n_gt;             // how many keys == T survive (highest indices)
+    int dummy = 0;
+    T2 = radix_select([&](int i) { return s_keys[i] == T ? (unsigned)(i + 1) : 0u; }, p.NA,
+                      need_eq, s_hist, s_bcast, &dummy);
+  }
+
+  // ---- phase 3: compact survivors + bitonic sort (ascending in (~key, ~index))
+  for (int i = tid; i < p.kpad; i += PT) s_sort[i] = ~0ull;
+  __syncthreads();
+  for (int a = tid; a < p.NA; a += PT) {
+    const unsigned k = s_keys[a];
+    const bool take = (k != 0u) && (k > T || (k == T && (unsigned)(a + 1) >= T2));
+    if (take) {
+      const int pos = atomicAdd(&s_cnt[1], 1);
+      s_sort[pos] = ((unsigned long long)(~k) << 32) | (unsigned)(~(unsigned)a);
+    }
+  }
+  __syncthreads();
+  for (int k = 2; k <= p.kpad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < p.kpad / 2; t += PT) {
+        const int i = 2 * t - (t & (j - 1));
+        const bool up = ((i & k) == 0);
+        const unsigned long long x = s_sort[i], y = s_sort[i + j];
+        if ((x > y) == up) { s_sort[i] = y; s_sort[i + j] = x; }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- phase 4: keep-list NMS over the K sorted candidates
+  int nkept = 0;
+  for (int c0 = 0; c0 < K && nkept < post; c0 += CHUNK) {
+    const int nc = min(CHUNK, K - c0);
+    if (tid < CHUNK) {
+      if (tid < nc) {
+        const unsigned long long e = s_sort[c0 + tid];
+        const int a = (int)(~(unsigned)(e & 0xffffffffull));
+        const float4 b = decode_anchor(p, img, a, im_h, im_w);
+        s_cbox[tid] = b;
+        s_carea[tid] = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f),
+                                 __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+        s_cidx[tid] = a;
+      }
+    }
+    __syncthreads();
+    // A: candidate (tid>>2) against kept entries tid&3, +4, +8, ...
+    {
+      const int cand = tid >> 2;
+      int sup = 0;
+      if (cand < nc) {
+        const float4 bj = s_cbox[cand];
+        const float aj = s_carea[cand];
+        for (int k = tid & 3; k < nkept; k += 4) {
+          if (iou_ge(s_kbox[k], s_karea[k], bj, aj, p.thr_ge)) { sup = 1; break; }
+        }
+      }
+      sup |= __shfl_xor_sync(0xffffffffu, sup, 1);
+      sup |= __shfl_xor_sync(0xffffffffu, sup, 2);
+      // lanes 0,4,8,...: 8 candidates per warp -> one byte of the alive bitmap
+      const unsigned bal = __ballot_sync(0xffffffffu, !sup && cand < nc);
+      if (lane == 0) {
+        unsigned byte = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) byte |= ((bal >> (4 * q)) & 1u) << q;
+        reinterpret_cast<unsigned char*>(s_alive)[warp] = (unsigned char)byte;
+      }
+    }
+    __syncthreads();
+    // B: column masks inside the chunk: word g of candidate j = alive i in [64g,64g+63], i<j,
+    //    that suppress j
+    {
+      const int j = tid >> 2, g = tid & 3;
+      unsigned long long word = 0;
+      const bool alive_j = (s_alive[j >> 5] >> (j & 31)) & 1u;
+      if (alive_j && 64 * g < j) {
+        unsigned long long aw = ((unsigned long long)s_alive[2 * g + 1] << 32) | s_alive[2 * g];
+        const int hi = j - 64 * g;   // bits below hi are earlier candidates
+        if (hi < 64) aw &= (1ull << hi) - 1ull;
+        const float4 bj = s_cbox[j];
+        const float aj = s_carea[j];
+        while (aw) {
+          const int bit = __ffsll((long long)aw) - 1;
+          aw &= aw - 1;
+          const int i = 64 * g + bit;
+          if (iou_ge(s_cbox[i], s_carea[i], bj, aj, p.thr_ge)) word |= 1ull << bit;
+        }
+      }
+      s_col[j * 4 + g] = word;
+    }
+    __syncthreads();
+    // C: warp 0 resolves the chunk, 32 candidates at a time
+    if (warp == 0) {
+      unsigned kw[CHUNK / 32];
+#pragma unroll
+      for (int sb = 0; sb < CHUNK / 32; ++sb) kw[sb] = 0;
+#pragma unroll
+      for (int sb = 0; sb < CHUNK / 32; ++sb) {
+        const int j = 32 * sb + lane;
+        const bool alive_j = (s_alive[sb] >> lane) & 1u;
+        const unsigned long long c0w = s_col[j * 4 + 0], c1w = s_col[j * 4 + 1];
+        const unsigned long long c2w = s_col[j * 4 + 2], c3w = s_col[j * 4 + 3];
+        const unsigned colw[8] = {(unsigned)c0w, (unsigned)(c0w >> 32), (unsigned)c1w,
+                                  (unsigned)(c1w >> 32), (unsigned)c2w, (unsigned)(c2w >> 32),
+                                  (unsigned)c3w, (unsigned)(c3w >> 32)};
+        bool dead = !alive_j;
+#pragma unroll
+        for (int q = 0; q < CHUNK / 32; ++q)
+          if (q < sb) dead = dead || ((colw[q] & kw[q]) != 0u);
+        unsigned own = 0;
+#pragma unroll
+        for (int q = 0; q < CHUNK / 32; ++q)
+          if (q == sb) own = colw[q];
+        unsigned Ks = __ballot_sync(0xffffffffu, !dead);
+        for (int it = 0; it < 32; ++it) {
+          const unsigned Kn = __ballot_sync(0xffffffffu, !dead && (own & Ks) == 0u);
+          if (Kn == Ks) break;
+          Ks = Kn;
+        }
+        kw[sb] = Ks;
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int sb = 0; sb < CHUNK / 32; ++sb) s_kmask[sb] = kw[sb];
+      }
+    }
+    __syncthreads();
+    // D: append the newly kept boxes (in order) and emit them
+    int total_new = 0;
+    {
+      int before = 0;   // kept candidates before mine in this chunk
+      const int j = tid;
+#pragma unroll
+      for (int sb = 0; sb < CHUNK / 32; ++sb) {
+        const unsigned m = s_kmask[sb];
+        total_new += __popc(m);
+        if (j < CHUNK) {
+          if (sb < (j >> 5)) before += __popc(m);
+          else if (sb == (j >> 5)) before += __popc(m & ((1u << (j & 31)) - 1u));
+        }
+      }
+      if (j < CHUNK && ((s_kmask[j >> 5] >> (j & 31)) & 1u)) {
+        const int pos = nkept + before;
+        if (pos < post) {
+          const float4 b = s_cbox[j];
+          s_kbox[pos] = b;
+          s_karea[pos] = s_carea[j];
+          float* r = p.rois + ((size_t)img * post + pos) * 5;
+          r[0] = (float)img; r[1] = b.x; r[2] = b.y; r[3] = b.z; r[4] = b.w;
+          const int a = s_cidx[j];
+          if (p.scores) p.scores[(size_t)img * post + pos] = key_to_float(s_keys[a]);
+          if (p.anchor_idx) p.anchor_idx[(size_t)img * post + pos] = a;
+        }
+      }
+    }
+    nkept = min(nkept + total_new, post);
+    __syncthreads();
+  }
+  // zero-fill the unused tail so the blob is deterministic
+  for (int i = nkept * 5 + tid; i < post * 5; i += PT) p.rois[(size_t)img * post * 5 + i] = 0.f;
+  for (int i = nkept + tid; i < post; i += PT) {
+    if (p.scores) p.scores[(size_t)img * post + i] = 0.f;
+    if (p.anchor_idx) p.anchor_idx[(size_t)img * post + i] = -1;
+  }
+  if (tid == 0) p.counts[img] = nkept;
+}
+
+size_t prop_smem_bytes(int NA, int kpad, int post) {
+  const size_t na_pad = (size_t)((NA + 3) & ~3);
+  size_t b = 0;
+  b += sizeof(unsigned long long) * (size_t)kpad;       // s_sort
+  b += sizeof(unsigned) * na_pad;                       // s_keys
+  b += sizeof(float4) * CHUNK;                          // s_cbox
+  b += sizeof(unsigned long long) * CHUNK * 4;          // s_col
+  b += sizeof(float) * CHUNK;                           // s_carea
+  b += sizeof(int) * CHUNK;                             // s_cidx
+  b += sizeof(unsigned) * (CHUNK / 32) * 2;             // s_alive, s_kmask
+  b += sizeof(unsigned) * (256 + 4) + sizeof(int) * 4;  // s_hist, s_bcast, s_cnt
+  b += sizeof(float4) * (size_t)post + sizeof(float) * (size_t)post;  // kept list
+  return b;
+}
+
+int pow2ceil(int v) {
+  int p = 2;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+extern "C" size_t wssdl_proposals_workspace_bytes(int, int, int, int, int, int) {
+  return 256;   // the fused kernel keeps all of its state in shared memory
+}
+
+extern "C" int wssdl_proposals(const float* cls_prob, const float* bbox_pred,
+                               const float* im_info, int info_stride, int B, int H, int W, int A,
+                               const float* base_anchors, int feat_stride, int pre_nms_topN,
+                               int post_nms_topN, double nms_thresh, float min_size, float* rois,
+                               float* scores, int* anchor_idx, int* counts, float* decoded,
+                               void* workspace, size_t workspace_bytes, wssdl_stream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  if (B < 0 || H <= 0 || W <= 0 || A <= 0 || info_stride < 3) return WSSDL_EINVAL;
+  if (B == 0) return WSSDL_OK;
+  if (!cls_prob || !bbox_pred || !im_info || !base_anchors || !rois || !counts) return WSSDL_EINVAL;
+  const long long NA = (long long)H * W * A;
+  if (A > MAX_ANCHORS || NA > 32768) return WSSDL_ELIMIT;
+  if (pre_nms_topN <= 0) pre_nms_topN = (int)NA;        // :130: no truncation
+  if (post_nms_topN <= 0 || post_nms_topN > 4096) return WSSDL_ELIMIT;
+  if (decoded && !aligned16(decoded)) return WSSDL_EALIGN;
+  const int kpad = pow2ceil((int)((long long)pre_nms_topN < NA ? pre_nms_topN : NA));
+  const size_t smem = prop_smem_bytes((int)NA, kpad, post_nms_topN);
+  if (smem > 227 * 1024) return WSSDL_ELIMIT;
+  cudaStream_t s = to_cuda(stream);
+  WSSDL_RETURN_IF_CUDA(cudaFuncSetAttribute(proposals_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+  PropParams p;
+  p.cls_prob = cls_prob; p.bbox_pred = bbox_pred; p.im_info = im_info;
+  p.info_stride = info_stride; p.H = H; p.W = W; p.A = A; p.NA = (int)NA;
+  p.feat_stride = feat_stride; p.pre_nms_topN = pre_nms_topN; p.post_nms_topN = post_nms_topN;
+  p.kpad = kpad;
+  float f = (float)nms_thresh;
+  if ((double)f < nms_thresh) f = nextafterf(f, INFINITY);
+  p.thr_ge = f;
+  p.min_size = min_size;
+  p.rois = rois; p.scores = scores; p.anchor_idx = anchor_idx; p.counts = counts;
+  p.decoded = decoded;
+  // base anchors: HOST pointer (generate_anchors runs on the host, as in the reference)
+  for (int i = 0; i < MAX_ANCHORS * 4; ++i) p.base[i] = i < 4 * A ? base_anchors[i] : 0.f;
+  proposals_kernel<<<B, PT, smem, s>>>(p);
+  WSSDL_CHECK_LAUNCH();
+  return WSSDL_OK;
+}

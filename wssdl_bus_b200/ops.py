@@ -1,0 +1,406 @@
+"""Tensor-level entry points: torch tensors carry the buffers, libwssdl_b200.so does the work.
+
+Every function enqueues on ``torch.cuda.current_stream()`` and returns device tensors
+without synchronising (unless documented otherwise).  numpy inputs are copied to the
+current CUDA device first.  Nothing here computes on the CPU: without CUDA or without the
+compiled library these functions raise.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (BIN_CPU_TRUNC, BIN_GPU_CEIL, BWD_ATOMIC, BWD_GATHER, IOU, IOU_UI,  # noqa: F401
+                   NMS_CONTAIN, NMS_GE_F64, NMS_GT_F32, WssdlError)
+
+_vp = ctypes.c_void_p
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("wssdl_bus_b200 needs a CUDA device (B200, sm_100a); there is no "
+                           "CPU fallback")
+
+
+def _cuda(x, dtype, device=None):
+    """numpy / torch (any device) -> contiguous CUDA tensor of `dtype`."""
+    _require_cuda()
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    elif not torch.is_tensor(x):
+        x = torch.as_tensor(np.asarray(x))
+    if device is None:
+        device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+
+
+def _ptr(t):
+    return _vp(t.data_ptr()) if (t is not None and t.numel() > 0) else _vp(None)
+
+
+def _stream(device):
+    return _vp(torch.cuda.current_stream(device).cuda_stream)
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes, device):
+    """Grow-only scratch per (device, stream); the library never allocates on its own."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _bin_mode(bin_mode):
+    if bin_mode in ("cpu", "cpu_trunc", BIN_CPU_TRUNC):
+        return BIN_CPU_TRUNC
+    if bin_mode in ("gpu", "gpu_ceil", BIN_GPU_CEIL):
+        return BIN_GPU_CEIL
+    raise ValueError("bin_mode must be 'cpu' (roi_pooling_op.cc) or 'gpu' (roi_pooling_op_gpu.cu.cc)")
+
+
+# ------------------------------------------------------------------ RoI pooling
+def roi_pool_forward(bottom, rois, pooled_height, pooled_width, spatial_scale, bin_mode="cpu",
+                     need_argmax=True):
+    """RoiPool forward.  bottom [B,H,W,C] f32 NHWC, rois [R,5] -> (top, argmax) [R,PH,PW,C].
+
+    Mirrors the op's checks (roi_pooling_op.cc:73-82, :97-102)."""
+    if pooled_height < 0:
+        raise ValueError("Need pooled_height >= 0, got %d" % pooled_height)
+    if pooled_width < 0:
+        raise ValueError("Need pooled_width >= 0, got %d" % pooled_width)
+    bottom = _cuda(bottom, torch.float32)
+    if bottom.dim() != 4:
+        raise ValueError("data must be 4-dimensional")
+    rois = _cuda(rois, torch.float32, bottom.device)
+    if rois.dim() != 2:
+        raise ValueError("rois must be 2-dimensional")
+    if rois.shape[1] != 5:
+        raise ValueError("rois must be [R,5] rows (batch, x1, y1, x2, y2)")
+    B, H, W, C = bottom.shape
+    R = rois.shape[0]
+    with torch.cuda.device(bottom.device):
+        top = torch.empty((R, pooled_height, pooled_width, C), dtype=torch.float32,
+                          device=bottom.device)
+        argmax = torch.empty_like(top, dtype=torch.int32) if need_argmax else None
+        rc = _lib.lib().wssdl_roi_pool_fwd(_ptr(bottom), _ptr(rois), B, H, W, C, R, pooled_height,
+                                           pooled_width, float(spatial_scale), _bin_mode(bin_mode),
+                                           _ptr(top), _ptr(argmax), _stream(bottom.device))
+    _lib.check(rc, "wssdl_roi_pool_fwd")
+    return top, argmax
+
+
+def roi_pool_backward(bottom_shape, rois, argmax, grad, pooled_height, pooled_width,
+                      spatial_scale, deterministic=False):
+    """RoiPoolGrad.  Returns bottom_diff [B,H,W,C] f32."""
+    grad = _cuda(grad, torch.float32)
+    argmax = _cuda(argmax, torch.int32, grad.device)
+    rois = _cuda(rois, torch.float32, grad.device)
+    if grad.dim() != 4:
+        raise ValueError("out_backprop must be 4-dimensional")
+    if argmax.dim() != 4:
+        raise ValueError("argmax_data must be 4-dimensional")
+    if rois.dim() != 2:
+        raise ValueError("rois must be 2-dimensional")
+    B, H, W, C = [int(v) for v in bottom_shape]
+    R = rois.shape[0]
+    if tuple(grad.shape) != (R, pooled_height, pooled_width, C) or grad.shape != argmax.shape:
+        raise ValueError("grad/argmax must be [R,PH,PW,C]")
+    with torch.cuda.device(grad.device):
+        out = torch.empty((B, H, W, C), dtype=torch.float32, device=grad.device)
+        rc = _lib.lib().wssdl_roi_pool_bwd(_ptr(grad), _ptr(argmax), _ptr(rois), B, H, W, C, R,
+                                           pooled_height, pooled_width, float(spatial_scale),
+                                           BWD_GATHER if deterministic else BWD_ATOMIC, _ptr(out),
+                                           _stream(grad.device))
+    _lib.check(rc, "wssdl_roi_pool_bwd")
+    return out
+
+
+class _RoiPoolFn(torch.autograd.Function):
+    """Gradient registration twin of roi_pooling_op_grad.py:24-44."""
+
+    @staticmethod
+    def forward(ctx, bottom, rois, ph, pw, scale, bin_mode, deterministic):
+        top, argmax = roi_pool_forward(bottom, rois, ph, pw, scale, bin_mode)
+        ctx.save_for_backward(rois, argmax)
+        ctx.meta = (tuple(bottom.shape), ph, pw, scale, deterministic)
+        ctx.mark_non_differentiable(argmax)
+        return top, argmax
+
+    @staticmethod
+    def backward(ctx, grad_top, _grad_argmax):
+        rois, argmax = ctx.saved_tensors
+        shape, ph, pw, scale, det = ctx.meta
+        g = roi_pool_backward(shape, rois, argmax, grad_top.contiguous(), ph, pw, scale, det)
+        return g, None, None, None, None, None, None
+
+
+def roi_pool(bottom_data, bottom_rois, pooled_height, pooled_width, spatial_scale, name=None,
+             bin_mode="cpu", deterministic_grad=False):
+    """Drop-in for roi_pooling_op.roi_pool (roi_pooling_op.py:6): -> (top_data, argmax)."""
+    del name
+    if torch.is_tensor(bottom_data) and bottom_data.requires_grad and torch.is_grad_enabled():
+        return _RoiPoolFn.apply(bottom_data, _cuda(bottom_rois, torch.float32, bottom_data.device),
+                                pooled_height, pooled_width, spatial_scale, bin_mode,
+                                deterministic_grad)
+    return roi_pool_forward(bottom_data, bottom_rois, pooled_height, pooled_width, spatial_scale,
+                            bin_mode)
+
+
+def roi_pool_grad(data, rois, argmax, grad, pooled_height, pooled_width, spatial_scale,
+                  deterministic=False):
+    """Drop-in for roi_pooling_op.roi_pool_grad (roi_pooling_op.py:7); `data` supplies the
+    bottom shape only, as in RoiPoolGradOp (roi_pooling_op.cc:372)."""
+    return roi_pool_backward(tuple(data.shape), rois, argmax, grad, pooled_height, pooled_width,
+                             spatial_scale, deterministic)
+
+
+# ------------------------------------------------------------------ NMS
+def nms_device(dets, thresh, mode=NMS_GE_F64, max_keep=0):
+    """dets: CUDA/numpy [N,>=5] f32.  Returns (keep i32 [min(N,max_keep or N)], num i32 [1],
+    status i32 [2]) on the device, no synchronisation."""
+    dets = _cuda(dets, torch.float32)
+    if dets.dim() != 2 or dets.shape[1] < 5:
+        raise ValueError("dets must be [N,5] rows (x1,y1,x2,y2,score)")
+    N = dets.shape[0]
+    dev = dets.device
+    with torch.cuda.device(dev):
+        cap = min(N, max_keep) if max_keep > 0 else N
+        keep = torch.empty((max(cap, 1),), dtype=torch.int32, device=dev)
+        misc = torch.zeros((4,), dtype=torch.int32, device=dev)
+        nbytes = _lib.lib().wssdl_nms_workspace_bytes(N)
+        ws = _workspace(nbytes, dev)
+        rc = _lib.lib().wssdl_nms(_ptr(dets), N, dets.shape[1], float(thresh), int(mode),
+                                  int(max_keep), _vp(keep.data_ptr()), _vp(misc.data_ptr()),
+                                  _vp(misc.data_ptr() + 4), _vp(ws.data_ptr()), ws.numel(),
+                                  _stream(dev))
+    _lib.check(rc, "wssdl_nms")
+    return keep[:cap], misc[0:1], misc[1:3]
+
+
+def nms(dets, thresh, mode=NMS_GE_F64, max_keep=0):
+    """cpu_nms-shaped call: returns a Python list of kept indices in descending-score
+    order.  numpy input goes through the host entry point of the C ABI (one H2D, one D2H);
+    CUDA tensors stay on the device until the final read."""
+    if isinstance(dets, np.ndarray) or (torch.is_tensor(dets) and not dets.is_cuda):
+        _require_cuda()
+        d = np.ascontiguousarray(dets.numpy() if torch.is_tensor(dets) else dets, dtype=np.float32)
+        if d.ndim != 2 or d.shape[1] < 5:
+            raise ValueError("dets must be [N,5] rows (x1,y1,x2,y2,score)")
+        n = d.shape[0]
+        if n == 0:
+            return []
+        keep = np.empty((n,), dtype=np.int32)
+        num = ctypes.c_int(0)
+        rc = _lib.lib().wssdl_nms_host(keep.ctypes.data_as(_vp), ctypes.byref(num),
+                                       d.ctypes.data_as(_vp), n, d.shape[1], float(thresh),
+                                       int(mode), int(max_keep), torch.cuda.current_device())
+        if rc == _lib.EZERODIV:
+            raise ZeroDivisionError("float division")
+        _lib.check(rc, "wssdl_nms_host")
+        return keep[:num.value].tolist()
+    keep, num, status = nms_device(dets, thresh, mode, max_keep)
+    if dets.shape[0] == 0:
+        return []
+    n, zero = int(num.item()), int(status[0].item())
+    if zero:
+        raise ZeroDivisionError("float division")
+    return keep[:n].tolist()
+
+
+def gpu_nms_sorted_host(sorted_dets, thresh, device_id=0):
+    """`_nms` twin (nms_kernel.cu:91): host array already sorted, '>' in fp32."""
+    _require_cuda()
+    d = np.ascontiguousarray(sorted_dets, dtype=np.float32)
+    n = d.shape[0]
+    if n == 0:
+        return np.zeros((0,), np.int32)
+    keep = np.empty((n,), dtype=np.int32)
+    num = ctypes.c_int(0)
+    rc = _lib.lib().wssdl_gpu_nms_host(keep.ctypes.data_as(_vp), ctypes.byref(num),
+                                       d.ctypes.data_as(_vp), n, d.shape[1], float(thresh),
+                                       int(device_id))
+    if rc == _lib.EZERODIV:
+        rc = _lib.OK        # the reference's CUDA path never raises
+    _lib.check(rc, "wssdl_gpu_nms_host")
+    return keep[:num.value]
+
+
+# ------------------------------------------------------------------ IoU
+def bbox_overlaps_device(boxes, query, kind=IOU, dtype=torch.float64):
+    boxes = _cuda(boxes, dtype)
+    query = _cuda(query, dtype, boxes.device)
+    if boxes.dim() != 2 or query.dim() != 2 or boxes.shape[1] < 4 or query.shape[1] < 4:
+        raise ValueError("boxes and query_boxes must be [N,4] / [K,4]")
+    if boxes.shape[1] != 4:
+        boxes = boxes[:, :4].contiguous()
+    if query.shape[1] != 4:
+        query = query[:, :4].contiguous()
+    N, K = boxes.shape[0], query.shape[0]
+    with torch.cuda.device(boxes.device):
+        out = torch.empty((N, K), dtype=dtype, device=boxes.device)
+        fn = (_lib.lib().wssdl_bbox_overlaps_f64 if dtype == torch.float64
+              else _lib.lib().wssdl_bbox_overlaps_f32)
+        rc = fn(_ptr(boxes), N, _ptr(query), K, kind, _ptr(out), _stream(boxes.device))
+    _lib.check(rc, "wssdl_bbox_overlaps")
+    return out
+
+
+def _np_out(fn):
+    def wrapped(boxes, query, *a, **k):
+        as_np = isinstance(boxes, np.ndarray)
+        out = fn(boxes, query, *a, **k)
+        return out.cpu().numpy() if as_np else out
+    return wrapped
+
+
+@_np_out
+def bbox_overlaps(boxes, query_boxes):
+    """utils.cython_bbox.bbox_overlaps: fp64 IoU matrix (numpy in -> numpy out)."""
+    return bbox_overlaps_device(boxes, query_boxes, IOU, torch.float64)
+
+
+@_np_out
+def bbox_overlaps_ui(boxes, query_boxes):
+    """utils.cython_bbox_ui.bbox_overlaps_ui: intersection / area(boxes[n]), fp64."""
+    return bbox_overlaps_device(boxes, query_boxes, IOU_UI, torch.float64)
+
+
+# ------------------------------------------------------------------ box transforms
+def bbox_transform_inv(boxes, deltas):
+    as_np = isinstance(deltas, np.ndarray)
+    deltas_t = _cuda(deltas, torch.float32)
+    boxes_t = _cuda(boxes, torch.float32, deltas_t.device)
+    if boxes_t.shape[0] == 0:
+        out = torch.zeros((0, deltas_t.shape[1]), dtype=torch.float32, device=deltas_t.device)
+        return out.cpu().numpy() if as_np else out
+    N, k4 = deltas_t.shape
+    if k4 % 4 != 0 or boxes_t.shape != (N, 4):
+        raise ValueError("boxes [N,4], deltas [N,4k]")
+    with torch.cuda.device(deltas_t.device):
+        out = torch.empty_like(deltas_t)
+        rc = _lib.lib().wssdl_bbox_transform_inv(_ptr(boxes_t), _ptr(deltas_t), N, k4 // 4,
+                                                 _ptr(out), _stream(deltas_t.device))
+    _lib.check(rc, "wssdl_bbox_transform_inv")
+    return out.cpu().numpy() if as_np else out
+
+
+def clip_boxes(boxes, im_shape):
+    """In place for CUDA tensors; numpy input is clipped on the device and copied back into
+    the same array (the reference mutates its argument, bbox_transform.py:69-75)."""
+    as_np = isinstance(boxes, np.ndarray)
+    t = _cuda(boxes, torch.float32)
+    N, k4 = t.shape
+    with torch.cuda.device(t.device):
+        rc = _lib.lib().wssdl_clip_boxes(_ptr(t), N, k4 // 4, float(im_shape[0]),
+                                         float(im_shape[1]), _stream(t.device))
+    _lib.check(rc, "wssdl_clip_boxes")
+    if as_np:
+        boxes[...] = t.cpu().numpy()
+        return boxes
+    if torch.is_tensor(boxes) and boxes.data_ptr() != t.data_ptr():
+        boxes.copy_(t)
+        return boxes
+    return t
+
+
+def bbox_transform(ex_rois, gt_rois):
+    as_np = isinstance(ex_rois, np.ndarray)
+    ex = _cuda(ex_rois, torch.float32)
+    gt = _cuda(gt_rois, torch.float32, ex.device)
+    ex = ex[:, :4].contiguous()
+    gt = gt[:, :4].contiguous()
+    N = ex.shape[0]
+    with torch.cuda.device(ex.device):
+        out = torch.empty((N, 4), dtype=torch.float32, device=ex.device)
+        rc = _lib.lib().wssdl_bbox_transform(_ptr(ex), _ptr(gt), N, _ptr(out), _stream(ex.device))
+    _lib.check(rc, "wssdl_bbox_transform")
+    return out.cpu().numpy() if as_np else out
+
+
+# ------------------------------------------------------------------ proposals
+def proposals(cls_prob, bbox_pred, im_info, base_anchors, feat_stride, pre_nms_topN,
+              post_nms_topN, nms_thresh, min_size, want_decoded=False):
+    """Batched fused proposal layer.  cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A] (NHWC),
+    im_info [B,>=3].  Returns dict of device tensors: rois [B*post,5], scores [B*post],
+    anchor_idx [B*post] i32, counts [B] i32 (+ decoded [B,H*W*A,4] when asked)."""
+    cls_prob = _cuda(cls_prob, torch.float32)
+    dev = cls_prob.device
+    bbox_pred = _cuda(bbox_pred, torch.float32, dev)
+    im_info = _cuda(im_info, torch.float32, dev)
+    if im_info.dim() == 1:
+        im_info = im_info.reshape(1, -1)
+    base = np.ascontiguousarray(base_anchors, dtype=np.float32)
+    A = base.shape[0]
+    B, H, W, C2 = cls_prob.shape
+    if C2 != 2 * A or tuple(bbox_pred.shape) != (B, H, W, 4 * A) or im_info.shape[0] != B:
+        raise ValueError("shape mismatch: cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A], im_info [B,3+]")
+    post = int(post_nms_topN)
+    if post <= 0:
+        raise ValueError("post_nms_topN must be positive on the device path")
+    with torch.cuda.device(dev):
+        rois = torch.empty((B * post, 5), dtype=torch.float32, device=dev)
+        scores = torch.empty((B * post,), dtype=torch.float32, device=dev)
+        aidx = torch.empty((B * post,), dtype=torch.int32, device=dev)
+        counts = torch.empty((B,), dtype=torch.int32, device=dev)
+        decoded = (torch.empty((B, H * W * A, 4), dtype=torch.float32, device=dev)
+                   if want_decoded else None)
+        ws = _workspace(256, dev)
+        rc = _lib.lib().wssdl_proposals(
+            _ptr(cls_prob), _ptr(bbox_pred), _ptr(im_info), im_info.shape[1], B, H, W, A,
+            base.ctypes.data_as(_vp), int(feat_stride), int(pre_nms_topN), post,
+            float(nms_thresh), float(min_size), _ptr(rois), _ptr(scores), _ptr(aidx),
+            _ptr(counts), _ptr(decoded), _vp(ws.data_ptr()), ws.numel(), _stream(dev))
+    _lib.check(rc, "wssdl_proposals")
+    out = dict(rois=rois, scores=scores, anchor_idx=aidx, counts=counts, post_nms_topN=post)
+    if want_decoded:
+        out["decoded"] = decoded
+    return out
+
+
+def compact_rois(out):
+    """[B*post,5] fixed-stride blob + counts -> the reference's concatenated (sum R,5) blob
+    (proposal_layer_tf_bus.py:144-146).  Synchronises (reads counts)."""
+    post = out["post_nms_topN"]
+    counts = out["counts"].cpu().numpy()
+    rois = out["rois"]
+    parts = [rois[b * post:b * post + int(c)] for b, c in enumerate(counts)]
+    return torch.cat(parts, dim=0) if parts else rois[:0]
+
+
+# ------------------------------------------------------------------ anchor labels
+def anchor_labels(gt_boxes, num_gt, im_info, H, W, base_anchors, feat_stride, dataset_mode=0,
+                  positive_overlap=0.7, negative_overlap=0.3, clobber_positives=False,
+                  want_max_overlap=True):
+    """Deterministic part of anchor_target_layer[_joint].  gt_boxes [B,max_gt,5] f32, num_gt
+    [B] i32, im_info [B,>=2].  Returns (labels [B,H*W*A] f32, argmax_gt i32, max_overlap f64)."""
+    gt_boxes = _cuda(gt_boxes, torch.float32)
+    dev = gt_boxes.device
+    num_gt = _cuda(num_gt, torch.int32, dev)
+    im_info = _cuda(im_info, torch.float32, dev)
+    if im_info.dim() == 1:
+        im_info = im_info.reshape(1, -1)
+    base = np.ascontiguousarray(base_anchors, dtype=np.float32)
+    A = base.shape[0]
+    B, max_gt, five = gt_boxes.shape
+    if five != 5 or num_gt.shape[0] != B or im_info.shape[0] != B:
+        raise ValueError("gt_boxes [B,max_gt,5], num_gt [B], im_info [B,2+]")
+    NA = H * W * A
+    with torch.cuda.device(dev):
+        labels = torch.empty((B, NA), dtype=torch.float32, device=dev)
+        argmax = torch.empty((B, NA), dtype=torch.int32, device=dev)
+        maxov = torch.empty((B, NA), dtype=torch.float64, device=dev) if want_max_overlap else None
+        nbytes = _lib.lib().wssdl_anchor_labels_workspace_bytes(B, H, W, A, max_gt)
+        ws = _workspace(nbytes, dev)
+        rc = _lib.lib().wssdl_anchor_labels(
+            _ptr(gt_boxes), _ptr(num_gt), max_gt, _ptr(im_info), im_info.shape[1], B, H, W, A,
+            base.ctypes.data_as(_vp), int(feat_stride), int(dataset_mode),
+            float(positive_overlap), float(negative_overlap), int(bool(clobber_positives)),
+            _ptr(labels), _ptr(argmax), _ptr(maxov), _vp(ws.data_ptr()), ws.numel(), _stream(dev))
+    _lib.check(rc, "wssdl_anchor_labels")
+    return labels, argmax, maxov

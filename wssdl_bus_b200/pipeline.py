@@ -1,0 +1,147 @@
+"""Batched detector hot path: RPN outputs + feature maps -> proposals -> RoI pooling.
+
+This is the composition the reference executes per image inside one `sess.run`
+(VGGnet_test_bus.py:57-62: proposal_layer -> roi_pool), batched over images and sharded by
+image across GPUs.  Images are independent on this path (proposal_layer_tf_bus.py:75 loops
+them, RoIs carry their batch index), so ranks never exchange data while computing; the only
+collective is one all-gather of the fixed-stride per-image detections for evaluation.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .fast_rcnn.config import cfg
+from .rpn_msr.generate_anchors import generate_anchors
+
+
+def shard_images(n_images, rank, world_size):
+    """Image i belongs to rank i mod world_size (round robin)."""
+    return np.arange(rank, n_images, world_size, dtype=np.int64)
+
+
+class HotPath:
+    """proposal_layer -> roi_pool for a batch of images resident on one GPU."""
+
+    def __init__(self, is_training=False, pooled_h=7, pooled_w=7, spatial_scale=1.0 / 16,
+                 feat_stride=16, anchor_scales=(8, 16, 32), pre_nms_topN=None, post_nms_topN=None,
+                 nms_thresh=None, min_size=None, bin_mode="cpu"):
+        c = cfg['TRAIN' if is_training else 'TEST']
+        self.pre = c.RPN_PRE_NMS_TOP_N if pre_nms_topN is None else pre_nms_topN
+        self.post = c.RPN_POST_NMS_TOP_N if post_nms_topN is None else post_nms_topN
+        self.thresh = c.RPN_NMS_THRESH if nms_thresh is None else nms_thresh
+        self.min_size = c.RPN_MIN_SIZE if min_size is None else min_size
+        self.pooled_h, self.pooled_w, self.scale = pooled_h, pooled_w, spatial_scale
+        self.feat_stride = feat_stride
+        self.base = generate_anchors(scales=np.array(anchor_scales))
+        self.bin_mode = bin_mode
+        # kernels launched by one run(): proposals + roi_pool_fwd
+        self.launches_per_run = 2
+
+    def run(self, feat, cls_prob, bbox_pred, im_info, need_argmax=True):
+        """Device tensors in, device tensors out, no synchronisation.
+        feat [B,H,W,C], cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A], im_info [B,3+]."""
+        p = ops.proposals(cls_prob, bbox_pred, im_info, self.base, self.feat_stride, self.pre,
+                          self.post, self.thresh, self.min_size)
+        top, argmax = ops.roi_pool_forward(feat, p["rois"], self.pooled_h, self.pooled_w,
+                                           self.scale, self.bin_mode, need_argmax)
+        p["top"], p["argmax"] = top, argmax
+        return p
+
+    def detections(self, p):
+        """Fixed-stride per-image detections [B, post, 5] (x1,y1,x2,y2,score) + counts [B]:
+        the tensors that are all-gathered."""
+        B = p["counts"].shape[0]
+        det = torch.cat([p["rois"][:, 1:5], p["scores"][:, None]], dim=1)
+        return det.reshape(B, self.post, 5), p["counts"]
+
+
+def all_gather_detections(det, counts, group=None):
+    """One all-gather of [n_local, post, 5] f32 + [n_local] i32 (NCCL over NVLink on GPUs,
+    gloo in the CPU tests).  Every rank must hold the same n_local (pad the last shard).
+    Returns ([world, n_local, post, 5], [world, n_local]); image of slot (r, j) is
+    j * world + r under shard_images()."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return det[None], counts[None]
+    n_local = det.shape[0]
+    # concatenated-along-dim-0 output: the form both NCCL and gloo accept
+    det_all = torch.empty((world * n_local,) + tuple(det.shape[1:]), dtype=det.dtype,
+                          device=det.device)
+    cnt_all = torch.empty((world * n_local,), dtype=counts.dtype, device=counts.device)
+    dist.all_gather_into_tensor(det_all, det.contiguous(), group=group)
+    dist.all_gather_into_tensor(cnt_all, counts.contiguous(), group=group)
+    return (det_all.reshape((world, n_local) + tuple(det.shape[1:])),
+            cnt_all.reshape(world, n_local))
+
+
+def unshard_detections(det_all, cnt_all, n_images):
+    """[world, n_local, ...] gathered slots -> per-image order [n_images, ...]."""
+    world, n_local = cnt_all.shape
+    det = det_all.transpose(0, 1).reshape((n_local * world,) + tuple(det_all.shape[2:]))
+    cnt = cnt_all.transpose(0, 1).reshape(n_local * world)
+    return det[:n_images], cnt[:n_images]
+
+
+class HostPipeline:
+    """End-to-end form of HotPath.run for HOST buffers (the shape of the reference's py_func
+    boundary, network.py:216): pinned host inputs are copied to the device in chunks of
+    images, computed, and every output (rois, scores, counts, pooled features, argmax) is
+    copied back to pinned host memory.  Two CUDA streams double-buffer the chunks so the
+    H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i."""
+
+    def __init__(self, hot, B, H, W, C, A, info_cols=3, chunk=32, device=None, need_argmax=True):
+        self.hot, self.B, self.chunk = hot, B, min(chunk, B)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.need_argmax = need_argmax
+        post, ph, pw = hot.post, hot.pooled_h, hot.pooled_w
+        pin = dict(pin_memory=True)
+        self.h_out = dict(
+            rois=torch.empty((B * post, 5), dtype=torch.float32, **pin),
+            scores=torch.empty((B * post,), dtype=torch.float32, **pin),
+            counts=torch.empty((B,), dtype=torch.int32, **pin),
+            top=torch.empty((B * post, ph, pw, C), dtype=torch.float32, **pin),
+        )
+        if need_argmax:
+            self.h_out["argmax"] = torch.empty((B * post, ph, pw, C), dtype=torch.int32, **pin)
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(2)]
+        n = self.chunk
+        dev = self.device
+        self.d_in = [dict(feat=torch.empty((n, H, W, C), device=dev),
+                          cls=torch.empty((n, H, W, 2 * A), device=dev),
+                          reg=torch.empty((n, H, W, 4 * A), device=dev),
+                          info=torch.empty((n, info_cols), device=dev)) for _ in range(2)]
+        self.h2d_bytes = 4 * B * (H * W * (C + 6 * A) + info_cols)
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.h_out.values())
+
+    def run(self, h_feat, h_cls, h_reg, h_info):
+        """Pinned host tensors in -> dict of pinned host tensors out.  Synchronises."""
+        post = self.hot.post
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+        for ci, b0 in enumerate(range(0, self.B, self.chunk)):
+            b1 = min(b0 + self.chunk, self.B)
+            n = b1 - b0
+            s = self.streams[ci % 2]
+            d = self.d_in[ci % 2]
+            with torch.cuda.stream(s):
+                d["feat"][:n].copy_(h_feat[b0:b1], non_blocking=True)
+                d["cls"][:n].copy_(h_cls[b0:b1], non_blocking=True)
+                d["reg"][:n].copy_(h_reg[b0:b1], non_blocking=True)
+                d["info"][:n].copy_(h_info[b0:b1], non_blocking=True)
+                p = self.hot.run(d["feat"][:n], d["cls"][:n], d["reg"][:n], d["info"][:n],
+                                 self.need_argmax)
+                # batch indices are chunk-local on the device; make them global for the host
+                rois = p["rois"]
+                rois[:, 0] += float(b0)
+                self.h_out["rois"][b0 * post:b1 * post].copy_(rois, non_blocking=True)
+                self.h_out["scores"][b0 * post:b1 * post].copy_(p["scores"], non_blocking=True)
+                self.h_out["counts"][b0:b1].copy_(p["counts"], non_blocking=True)
+                self.h_out["top"][b0 * post:b1 * post].copy_(p["top"], non_blocking=True)
+                if self.need_argmax:
+                    self.h_out["argmax"][b0 * post:b1 * post].copy_(p["argmax"], non_blocking=True)
+        for s in self.streams:
+            cur.wait_stream(s)
+        cur.synchronize()
+        return self.h_out
