@@ -167,8 +167,8 @@ int wssdl_bbox_transform(const float* ex_rois, const float* gt_rois, int N, floa
  * pre_nms_topN <= 0 means "no truncation" (:130).
  * Limits (WSSDL_ELIMIT otherwise): H*W*A <= 32768 anchors per image, 0 < post_nms_topN <=
  * 4096, and the per-image state must fit one SM's shared memory:
- * 8*pow2ceil(min(pre_nms_topN, H*W*A)) + 4*H*W*A + 20*post_nms_topN + 16 KB <= 227 KB
- * (the reference's shapes: 17100 anchors with 6000->300 or 12000->2000 fit).
+ * 8*pow2ceil(min(pre_nms_topN, H*W*A)) + max(4*H*W*A, 20*post_nms_topN + 17 KB) + 1 KB
+ * <= 227 KB (the reference's shapes, 17100 anchors with 6000->300 or 12000->2000, fit).
  */
 size_t wssdl_proposals_workspace_bytes(int B, int H, int W, int A, int pre_nms_topN,
                                        int post_nms_topN);

@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 nproc > gpurun_out/host.txt; free -g >> gpurun_out/host.txt
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
-timeout 1500 python -m pytest tests -q -m gpu -x --timeout 600 ${PYTEST_ARGS} > gpurun_out/pytest_gpu.log 2>&1
+timeout 1500 python -m pytest tests -q -m gpu --maxfail=10 --timeout 600 ${PYTEST_ARGS} > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 tail -25 gpurun_out/pytest_gpu.log
 if [ "${SKIP_BENCH}" != "1" ]; then

@@ -174,20 +174,23 @@ __device__ unsigned radix_select(KeyFn key_at, int n, int K, unsigned* s_hist /*
 __global__ void __launch_bounds__(PT, 1)
 proposals_kernel(const PropParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: sort buffer (kpad u64) | keys (NA u32) | per-chunk NMS state | kept list
+  // layout: sort buffer (kpad u64) | histogram/scalars | UNION { keys (NA u32), live in phases
+  // 1-3 ; per-chunk NMS state + kept list, live in phase 4 }.  The score keys are dead once
+  // the survivors sit in the sort buffer (which carries ~key in its high word).
   unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem_raw);
-  unsigned* s_keys = reinterpret_cast<unsigned*>(s_sort + p.kpad);
-  const int na_pad = (p.NA + 3) & ~3;
-  float4* s_cbox = reinterpret_cast<float4*>(s_keys + na_pad);                 // [CHUNK]
+  unsigned* s_hist = reinterpret_cast<unsigned*>(s_sort + p.kpad);             // [256]
+  unsigned* s_bcast = s_hist + 256;                                            // [4]
+  int* s_cnt = reinterpret_cast<int*>(s_bcast + 4);                            // [4]
+  unsigned char* s_union = reinterpret_cast<unsigned char*>(s_cnt + 4);
+  unsigned* s_keys = reinterpret_cast<unsigned*>(s_union);                     // [NA]
+  float4* s_cbox = reinterpret_cast<float4*>(s_union);                         // [CHUNK]
   unsigned long long* s_col = reinterpret_cast<unsigned long long*>(s_cbox + CHUNK);  // [CHUNK][4]
   float* s_carea = reinterpret_cast<float*>(s_col + CHUNK * 4);                // [CHUNK]
   int* s_cidx = reinterpret_cast<int*>(s_carea + CHUNK);                       // [CHUNK]
-  unsigned* s_alive = reinterpret_cast<unsigned*>(s_cidx + CHUNK);             // [CHUNK/32]
+  unsigned* s_ckey = reinterpret_cast<unsigned*>(s_cidx + CHUNK);              // [CHUNK]
+  unsigned* s_alive = s_ckey + CHUNK;                                          // [CHUNK/32]
   unsigned* s_kmask = s_alive + CHUNK / 32;                                    // [CHUNK/32]
-  unsigned* s_hist = s_kmask + CHUNK / 32;                                     // [256]
-  unsigned* s_bcast = s_hist + 256;                                            // [4]
-  int* s_cnt = reinterpret_cast<int*>(s_bcast + 4);                            // [4]
-  float4* s_kbox = reinterpret_cast<float4*>(s_cnt + 4);                       // [post]
+  float4* s_kbox = reinterpret_cast<float4*>(s_kmask + CHUNK / 32);            // [post]
   float* s_karea = reinterpret_cast<float*>(s_kbox + p.post_nms_topN);         // [post]
 
   const int img = blockIdx.x;
@@ -267,6 +270,7 @@ proposals_kernel(const PropParams p) {
         s_carea[tid] = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f),
                                  __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
         s_cidx[tid] = a;
+        s_ckey[tid] = ~(unsigned)(e >> 32);
       }
     }
     __syncthreads();
@@ -374,7 +378,7 @@ proposals_kernel(const PropParams p) {
           float* r = p.rois + ((size_t)img * post + pos) * 5;
           r[0] = (float)img; r[1] = b.x; r[2] = b.y; r[3] = b.z; r[4] = b.w;
           const int a = s_cidx[j];
-          if (p.scores) p.scores[(size_t)img * post + pos] = key_to_float(s_keys[a]);
+          if (p.scores) p.scores[(size_t)img * post + pos] = key_to_float(s_ckey[j]);
           if (p.anchor_idx) p.anchor_idx[(size_t)img * post + pos] = a;
         }
       }
@@ -393,17 +397,14 @@ proposals_kernel(const PropParams p) {
 
 size_t prop_smem_bytes(int NA, int kpad, int post) {
   const size_t na_pad = (size_t)((NA + 3) & ~3);
-  size_t b = 0;
-  b += sizeof(unsigned long long) * (size_t)kpad;       // s_sort
-  b += sizeof(unsigned) * na_pad;                       // s_keys
-  b += sizeof(float4) * CHUNK;                          // s_cbox
-  b += sizeof(unsigned long long) * CHUNK * 4;          // s_col
-  b += sizeof(float) * CHUNK;                           // s_carea
-  b += sizeof(int) * CHUNK;                             // s_cidx
-  b += sizeof(unsigned) * (CHUNK / 32) * 2;             // s_alive, s_kmask
-  b += sizeof(unsigned) * (256 + 4) + sizeof(int) * 4;  // s_hist, s_bcast, s_cnt
-  b += sizeof(float4) * (size_t)post + sizeof(float) * (size_t)post;  // kept list
-  return b;
+  size_t fixed = sizeof(unsigned long long) * (size_t)kpad;          // s_sort
+  fixed += sizeof(unsigned) * (256 + 4) + sizeof(int) * 4;           // s_hist, s_bcast, s_cnt
+  const size_t keys = sizeof(unsigned) * na_pad;                     // phases 1-3
+  size_t nms = sizeof(float4) * CHUNK + sizeof(unsigned long long) * CHUNK * 4 +
+               sizeof(float) * CHUNK + sizeof(int) * CHUNK + sizeof(unsigned) * CHUNK +
+               sizeof(unsigned) * (CHUNK / 32) * 2;                  // per-chunk state
+  nms += (sizeof(float4) + sizeof(float)) * (size_t)post;            // kept list
+  return fixed + (keys > nms ? keys : nms);
 }
 
 int pow2ceil(int v) {
