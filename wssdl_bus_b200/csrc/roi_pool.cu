@@ -18,6 +18,8 @@
 //     shared memory to capture; loads go through the read-only path (ld.global.nc) and
 //     the outputs, never re-read by this kernel, use st.global.cs so they do not evict
 //     the feature map from L2.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -26,21 +28,42 @@ template <int VEC> struct VecT;
 template <> struct VecT<4> { using F = float4; using I = int4; };
 template <> struct VecT<1> { using F = float;  using I = int; };
 
-__device__ __forceinline__ void upd(float v, int cell_base, float& m, int& mi) {
+__device__ __forceinline__ void upd(float v, int cell, float& m, int& mi) {
   // strict '>' (cc:187): NaN never wins, first maximum wins
-  if (v > m) { m = v; mi = cell_base; }
+  if (v > m) { m = v; mi = cell; }
+}
+__device__ __forceinline__ void upd4(const float4 v, int cell, float (&m)[4], int (&mi)[4]) {
+  upd(v.x, cell, m[0], mi[0]); upd(v.y, cell, m[1], mi[1]);
+  upd(v.z, cell, m[2], mi[2]); upd(v.w, cell, m[3], mi[3]);
 }
 
-template <int VEC, int BIN_MODE>
+// The kernel is issue-slot bound before it is HBM bound (ncu, profiles/r01_*: the first
+// version ran at 82 % issue utilisation and 48 % DRAM), so the loops are written for
+// instruction count:
+//   - no channel loop: one thread = one channel vector (grid.y covers C > 4*blockDim.x);
+//   - one 64-bit running pointer per row, constant strides folded into immediates when C is a
+//     compile-time value (CVT = C/4 for the common C = 512 / 1024, 0 = runtime);
+//   - the scan tracks cell*C (+= C per cell) and each channel's index register starts at
+//     -1 - c, so the flat index (h*W+w)*C + c is a single add per output and "nothing
+//     pooled" comes out as -1 without a select;
+//   - 3 instructions (FSETP, FSEL, SEL) per channel and cell, which is the floor for a
+//     first-maximum argmax.
+//   - VPT channel vectors per thread (lanes cv and cv + CV/VPT): the per-bin / per-row
+//     bookkeeping is paid once for 4*VPT channels.
+template <int VEC, int BIN_MODE, int CVT, int VPT>
 __global__ void __launch_bounds__(256)
 roi_pool_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ rois,
-                    int B, int H, int W, int C, int PH, int PW, float spatial_scale,
+                    int B, int H, int W, int C_rt, int PH, int PW, float spatial_scale,
                     float* __restrict__ top, int* __restrict__ argmax) {
   using F = typename VecT<VEC>::F;
   using I = typename VecT<VEC>::I;
+  const int C = CVT ? CVT * VEC : C_rt;
+  const int CV = CVT ? CVT : C_rt / VEC;           // vector lanes per cell
+  const int CVH = CV / VPT;                        // lanes owned by "vector slot" 0
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cv >= CVH) return;
   const int n = blockIdx.x / PH;
   const int ph = blockIdx.x - n * PH;
-  const int CV = C / VEC;
 
   const RoiCells g = roi_cells(rois + (size_t)n * 5, spatial_scale, PH, PW);
   const bool bad_batch = (g.batch < 0) || (g.batch >= B);
@@ -49,68 +72,80 @@ roi_pool_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
   int hend = bin_hi<BIN_MODE>(ph, g.bin_h);
   hstart = min(max(hstart + g.start_h, 0), H);   // cc:173-176
   hend = min(max(hend + g.start_h, 0), H);
+  const bool row_empty = (hend <= hstart) || bad_batch;
+  const int nh = hend - hstart;
 
-  const float* __restrict__ img = bottom + (size_t)(bad_batch ? 0 : g.batch) * H * W * C;
-  const size_t out_row = ((size_t)n * PH + ph) * PW;
+  // this thread's lane in row hstart, column 0 of its image
+  const F* __restrict__ img = reinterpret_cast<const F*>(bottom) +
+      ((size_t)(bad_batch ? 0 : g.batch) * H + (row_empty ? 0 : hstart)) * (size_t)(W * CV) + cv;
+  const int row_stride = W * CV;                   // in vectors
+  const int c = cv * VEC;
+  const size_t out0 = (((size_t)n * PH + ph) * PW + threadIdx.y) * CV + cv;   // vector units
+  F* __restrict__ top_p = reinterpret_cast<F*>(top) + out0;
+  I* __restrict__ arg_p = reinterpret_cast<I*>(argmax) + out0;
+  const int out_step = blockDim.y * CV;
 
-  for (int pw = threadIdx.y; pw < PW; pw += blockDim.y) {
+  for (int pw = threadIdx.y; pw < PW; pw += blockDim.y, top_p += out_step, arg_p += out_step) {
     int wstart = bin_lo<BIN_MODE>(pw, g.bin_w);
     int wend = bin_hi<BIN_MODE>(pw, g.bin_w);
     wstart = min(max(wstart + g.start_w, 0), W);
     wend = min(max(wend + g.start_w, 0), W);
-    const bool is_empty = (hend <= hstart) || (wend <= wstart) || bad_batch;
+    const bool is_empty = row_empty || (wend <= wstart);
+    const int nw = wend - wstart;
 
-    for (int cv = threadIdx.x; cv < CV; cv += blockDim.x) {
-      const int c = cv * VEC;
-      float m[VEC];
-      int mi[VEC];
+    float m[VPT][4];
+    int mi[VPT][4];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) { m[k] = is_empty ? 0.f : -FLT_MAX; mi[k] = -1; }  // cc:180-182
-      if (!is_empty) {
-        for (int h = hstart; h < hend; ++h) {
-          int cell = (h * W + wstart) * C;
-          const float* __restrict__ p = img + cell + c;
-          int w = wstart;
-          // two cells per trip: both loads are issued before the dependent compares
-          for (; w + 1 < wend; w += 2, p += 2 * C, cell += 2 * C) {
-            F v0 = __ldg(reinterpret_cast<const F*>(p));
-            F v1 = __ldg(reinterpret_cast<const F*>(p + C));
+    for (int v = 0; v < VPT; ++v)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                // cc:180-182
+        m[v][k] = is_empty ? 0.f : -FLT_MAX;
+        mi[v][k] = -1 - (c + v * CVH * VEC) - k;   // + channel at the end => -1 if never updated
+      }
+    if (!is_empty) {
+      const F* __restrict__ prow = img + wstart * CV;
+      int cellC0 = (hstart * W + wstart) * C;      // (h*W+w)*C of the row start
+      for (int r = nh; r > 0; --r, prow += row_stride, cellC0 += W * C) {
+        const F* __restrict__ p = prow;
+        int cellC = cellC0;
+        int left = nw;
+        // two cells per trip: all loads are issued before the dependent compares
+        for (; left >= 2; left -= 2, p += 2 * CV, cellC += 2 * C) {
+          F v0[VPT], v1[VPT];
+#pragma unroll
+          for (int v = 0; v < VPT; ++v) { v0[v] = __ldg(p + v * CVH); v1[v] = __ldg(p + CV + v * CVH); }
+#pragma unroll
+          for (int v = 0; v < VPT; ++v) {
             if constexpr (VEC == 4) {
-              upd(v0.x, cell, m[0], mi[0]); upd(v0.y, cell, m[1], mi[1]);
-              upd(v0.z, cell, m[2], mi[2]); upd(v0.w, cell, m[3], mi[3]);
-              upd(v1.x, cell + C, m[0], mi[0]); upd(v1.y, cell + C, m[1], mi[1]);
-              upd(v1.z, cell + C, m[2], mi[2]); upd(v1.w, cell + C, m[3], mi[3]);
+              upd4(v0[v], cellC, m[v], mi[v]);
+              upd4(v1[v], cellC + C, m[v], mi[v]);
             } else {
-              upd(v0, cell, m[0], mi[0]);
-              upd(v1, cell + C, m[0], mi[0]);
+              upd(v0[v], cellC, m[v][0], mi[v][0]);
+              upd(v1[v], cellC + C, m[v][0], mi[v][0]);
             }
           }
-          if (w < wend) {
-            F v0 = __ldg(reinterpret_cast<const F*>(p));
-            if constexpr (VEC == 4) {
-              upd(v0.x, cell, m[0], mi[0]); upd(v0.y, cell, m[1], mi[1]);
-              upd(v0.z, cell, m[2], mi[2]); upd(v0.w, cell, m[3], mi[3]);
-            } else {
-              upd(v0, cell, m[0], mi[0]);
-            }
+        }
+        if (left) {
+#pragma unroll
+          for (int v = 0; v < VPT; ++v) {
+            const F v0 = __ldg(p + v * CVH);
+            if constexpr (VEC == 4) upd4(v0, cellC, m[v], mi[v]);
+            else upd(v0, cellC, m[v][0], mi[v][0]);
           }
         }
       }
-      // mi holds the cell base (h*W+w)*C; the flat index adds the channel (cc:186)
-      const size_t o = (out_row + pw) * C + c;
+    }
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int cc = c + v * CVH * VEC;
       if constexpr (VEC == 4) {
-        __stcs(reinterpret_cast<float4*>(top + o), make_float4(m[0], m[1], m[2], m[3]));
-        if (argmax != nullptr) {
-          int4 a;
-          a.x = mi[0] < 0 ? -1 : mi[0] + c;
-          a.y = mi[1] < 0 ? -1 : mi[1] + c + 1;
-          a.z = mi[2] < 0 ? -1 : mi[2] + c + 2;
-          a.w = mi[3] < 0 ? -1 : mi[3] + c + 3;
-          __stcs(reinterpret_cast<int4*>(argmax + o), a);
-        }
+        __stcs(top_p + v * CVH, make_float4(m[v][0], m[v][1], m[v][2], m[v][3]));
+        if (argmax != nullptr)
+          __stcs(arg_p + v * CVH, make_int4(mi[v][0] + cc, mi[v][1] + cc + 1, mi[v][2] + cc + 2,
+                                            mi[v][3] + cc + 3));
       } else {
-        __stcs(top + o, m[0]);
-        if (argmax != nullptr) __stcs(argmax + o, mi[0] < 0 ? -1 : mi[0] + c);
+        __stcs(top_p + v * CVH, m[v][0]);
+        if (argmax != nullptr) __stcs(arg_p + v * CVH, mi[v][0] + cc);
       }
     }
   }
@@ -362,20 +397,36 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
   const bool vec4 = (C % 4 == 0) && aligned16(bottom) && aligned16(top) &&
                     (argmax == nullptr || aligned16(argmax));
   const int CV = vec4 ? C / 4 : C;
-  dim3 block(pick_block_x(CV), 1);
+  // channel vectors per thread: 2 when the channel count allows it (tuning knob for
+  // experiments: WSSDL_ROI_FWD_VPT=1|2)
+  static const int vpt_env = [] { const char* e = getenv("WSSDL_ROI_FWD_VPT"); return e ? atoi(e) : 0; }();
+  int vpt = (vec4 && CV % 64 == 0) ? 2 : 1;
+  if (vpt_env == 1) vpt = 1;
+  const int lanes = CV / vpt;
+  dim3 block(pick_block_x(lanes), 1);
   block.y = max(1, min(PW, 128 / (int)block.x));
-  dim3 grid((unsigned)(R * PH));
+  dim3 grid((unsigned)(R * PH), (unsigned)ceil_div(lanes, block.x));
   cudaStream_t s = to_cuda(stream);
-#define LAUNCH_FWD(V, M)                                                                     \
-  roi_pool_fwd_kernel<V, M><<<grid, block, 0, s>>>(bottom, rois, B, H, W, C, PH, PW,         \
-                                                   spatial_scale, top, argmax)
-  if (vec4) {
-    if (bin_mode == WSSDL_BIN_CPU_TRUNC) LAUNCH_FWD(4, WSSDL_BIN_CPU_TRUNC);
-    else LAUNCH_FWD(4, WSSDL_BIN_GPU_CEIL);
+#define LAUNCH_FWD(V, M, CVT, VPT)                                                            \
+  roi_pool_fwd_kernel<V, M, CVT, VPT><<<grid, block, 0, s>>>(bottom, rois, B, H, W, C, PH, PW, \
+                                                             spatial_scale, top, argmax)
+#define LAUNCH_FWD_MODE(V, CVT, VPT)                                                          \
+  do {                                                                                        \
+    if (bin_mode == WSSDL_BIN_CPU_TRUNC) LAUNCH_FWD(V, WSSDL_BIN_CPU_TRUNC, CVT, VPT);        \
+    else LAUNCH_FWD(V, WSSDL_BIN_GPU_CEIL, CVT, VPT);                                         \
+  } while (0)
+  if (vec4 && vpt == 2) {
+    if (C == 512) LAUNCH_FWD_MODE(4, 128, 2);         // VGG-16 conv5_3
+    else if (C == 1024) LAUNCH_FWD_MODE(4, 256, 2);   // ResNet C4
+    else LAUNCH_FWD_MODE(4, 0, 2);
+  } else if (vec4) {
+    if (C == 512) LAUNCH_FWD_MODE(4, 128, 1);
+    else if (C == 1024) LAUNCH_FWD_MODE(4, 256, 1);
+    else LAUNCH_FWD_MODE(4, 0, 1);
   } else {
-    if (bin_mode == WSSDL_BIN_CPU_TRUNC) LAUNCH_FWD(1, WSSDL_BIN_CPU_TRUNC);
-    else LAUNCH_FWD(1, WSSDL_BIN_GPU_CEIL);
+    LAUNCH_FWD_MODE(1, 0, 1);
   }
+#undef LAUNCH_FWD_MODE
 #undef LAUNCH_FWD
   WSSDL_CHECK_LAUNCH();
   return WSSDL_OK;
