@@ -55,13 +55,21 @@ const char* wssdl_error_string(int code);   /* static string, also for cudaError
  *             WSSDL_BIN_GPU_CEIL reproduces the CUDA op (roi_pooling_op_gpu.cu.cc:51-58).
  * A RoI whose batch index is outside [0,B) yields top=0/argmax=-1 (the reference reads
  * out of bounds).  16-byte aligned pointers and C%4==0 select the vectorised kernels;
- * anything else runs the scalar variant of the same kernel.
+ * anything else runs the scalar variant of the direct kernel.
+ * workspace   optional scratch of wssdl_roi_pool_fwd_workspace_bytes(B, R) bytes (device,
+ *             4-byte aligned; may be NULL).  With it, batches of more than 4096 RoIs can
+ *             use the shared-memory-resident kernel (RoIs are counting-sorted by image into
+ *             the workspace first); without it they run the direct kernel.  Results are
+ *             identical either way.
  */
 enum { WSSDL_BIN_CPU_TRUNC = 0, WSSDL_BIN_GPU_CEIL = 1 };
 
+size_t wssdl_roi_pool_fwd_workspace_bytes(int B, int R);
+
 int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B, int H, int W, int C,
                        int R, int PH, int PW, float spatial_scale, int bin_mode,
-                       float* top, int* argmax, wssdl_stream_t stream);
+                       float* top, int* argmax, void* workspace, size_t workspace_bytes,
+                       wssdl_stream_t stream);
 
 /* bwd_mode WSSDL_BWD_ATOMIC: zero-fill + scatter through argmax with fp32 atomics
  *            (fast; summation order free => equal to the reference within 1e-5 rel;

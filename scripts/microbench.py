@@ -99,13 +99,31 @@ def main():
     only = set(args.only.split(",")) if args.only else None
 
     def want(name):
-        return (only is None and name != "roi4") or (only is not None and name in only)
+        return (only is None and name not in ("roi4", "roicmp")) or (only is not None and name in only)
 
     emit(out, op="env", gpu=torch.cuda.get_device_name(0), peak_gbs=PEAK,
          vpt=os.environ.get("WSSDL_ROI_FWD_VPT", "default"), occ=os.environ.get("WSSDL_ROI_FWD_OCC", "default"))
     if want("roi4"):
         r256 = realistic_rois(256)
         bench_roi(out, "C4 256 images x 300 proposal RoIs", 256, 512, 7, 7, r256, bwd=False)
+    if want("roicmp"):
+        # direct vs tiled forward kernel on every BASELINE shape (env knobs are read per call)
+        r1 = realistic_rois(1)
+        r256 = realistic_rois(256)
+        ru = torch.from_numpy(syn.rois_for_pool(5, 16 * 300, 16)).cuda()
+        ru = ru[torch.argsort(ru[:, 0], stable=True)].contiguous()
+        for kern, st in (("direct", "1"), ("tiled", "1"), ("tiled", "0")):
+            os.environ["WSSDL_ROI_FWD_KERNEL"] = kern
+            os.environ["WSSDL_ROI_FWD_STREAM_ST"] = st
+            tag = "[%s st=%s] " % (kern, st)
+            bench_roi(out, tag + "C4 256x300", 256, 512, 7, 7, r256, bwd=False)
+            bench_roi(out, tag + "C4 256x300 GPU_CEIL", 256, 512, 7, 7, r256, mode="gpu", bwd=False)
+            bench_roi(out, tag + "C1 1x300", 1, 512, 7, 7, r1, bwd=False)
+            bench_roi(out, tag + "C2 1x128", 1, 512, 7, 7, r1[:128].contiguous(), bwd=False)
+            bench_roi(out, tag + "16x300 7x7 C512", 16, 512, 7, 7, realistic_rois(16), bwd=False)
+            bench_roi(out, tag + "C3 16x1024 4800 RoIs 14x14", 16, 1024, 14, 14, ru, bwd=False)
+        os.environ.pop("WSSDL_ROI_FWD_KERNEL")
+        os.environ.pop("WSSDL_ROI_FWD_STREAM_ST")
     if want("roi"):
         r1 = realistic_rois(1)
         bench_roi(out, "C1 single image (300 proposal RoIs)", 1, 512, 7, 7, r1)

@@ -55,9 +55,9 @@ def test_binding_table_matches_header(built_lib):
 def test_argument_validation_without_gpu(built_lib):
     lib = built_lib.lib()
     # negative sizes / bad enums are rejected before any CUDA call
-    assert lib.wssdl_roi_pool_fwd(None, None, 1, 2, 2, 4, -1, 7, 7, 0.0625, 0, None, None, None) == built_lib.EINVAL
-    assert lib.wssdl_roi_pool_fwd(None, None, 1, 2, 2, 4, 1, 7, 7, 0.0625, 9, None, None, None) == built_lib.EINVAL
-    assert lib.wssdl_roi_pool_fwd(None, None, 1, 2, 2, 4, 0, 7, 7, 0.0625, 0, None, None, None) == built_lib.OK
+    assert lib.wssdl_roi_pool_fwd(None, None, 1, 2, 2, 4, -1, 7, 7, 0.0625, 0, None, None, None, 0, None) == built_lib.EINVAL
+    assert lib.wssdl_roi_pool_fwd(None, None, 1, 2, 2, 4, 1, 7, 7, 0.0625, 9, None, None, None, 0, None) == built_lib.EINVAL
+    assert lib.wssdl_roi_pool_fwd(None, None, 1, 2, 2, 4, 0, 7, 7, 0.0625, 0, None, None, None, 0, None) == built_lib.OK
     assert lib.wssdl_bbox_overlaps_f64(None, 0, None, 5, 0, None, None) == built_lib.OK
     assert lib.wssdl_bbox_overlaps_f64(None, 3, None, 5, 7, None, None) == built_lib.EINVAL
 

@@ -13,6 +13,15 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-5
 
 
+@pytest.fixture(params=["direct", "tiled"])
+def fwd_kernel(request, monkeypatch):
+    """Forces one of the two forward kernels (roi_pool.cu: direct = one CTA per output row
+    reading L2; tiled = shared-memory resident channel slice).  Shapes the tiled kernel
+    does not take (C % 16 != 0, misaligned pointers) fall through to the direct one."""
+    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", request.param)
+    return request.param
+
+
 def _fwd_both(oracle_mod, bottom, rois, PH, PW, scale, mode):
     want_top, want_arg = oracle_mod.clib.roi_pool_fwd(bottom, rois, PH, PW, scale,
                                                       bin_mode=0 if mode == "cpu" else 1)
@@ -21,7 +30,7 @@ def _fwd_both(oracle_mod, bottom, rois, PH, PW, scale, mode):
 
 
 @pytest.mark.parametrize("mode", ["cpu", "gpu"])
-def test_fwd_c1_shapes_bit_exact(oracle_mod, mode):
+def test_fwd_c1_shapes_bit_exact(oracle_mod, mode, fwd_kernel):
     c = syn.C1
     bottom = syn.feature_map(0, c["B"], c["H"], c["W"], c["C"])
     rois = syn.rois_for_pool(1, 300)
@@ -30,7 +39,7 @@ def test_fwd_c1_shapes_bit_exact(oracle_mod, mode):
 
 
 @pytest.mark.parametrize("mode", ["cpu", "gpu"])
-def test_fwd_adversarial_rois_bit_exact(oracle_mod, mode):
+def test_fwd_adversarial_rois_bit_exact(oracle_mod, mode, fwd_kernel):
     B, H, W, C = 2, 38, 50, 64
     bottom = syn.feature_map(2, B, H, W, C)
     bottom[0, 3:9, 4:11] = -np.inf                     # cells that can never win
@@ -43,7 +52,7 @@ def test_fwd_adversarial_rois_bit_exact(oracle_mod, mode):
 
 
 @pytest.mark.parametrize("C", [3, 5, 32, 100, 1024])
-def test_fwd_channel_counts_and_scalar_path(oracle_mod, C):
+def test_fwd_channel_counts_and_scalar_path(oracle_mod, C, fwd_kernel):
     # C=3 is the reference's own smoke shape (roi_pooling_op_test.py: 32x100x100x3, scale 1/3)
     B, H, W = 2, 20, 24
     bottom = syn.feature_map(4, B, H, W, C)
@@ -60,6 +69,69 @@ def test_fwd_misaligned_pointer_uses_scalar_kernel(oracle_mod):
     view = buf[1:].view(B, H, W, C)                    # 4-byte aligned only
     view.copy_(torch.from_numpy(bottom))
     top, arg = ops.roi_pool_forward(view, rois, 7, 7, 1 / 16.)
+    wt, wa = oracle_mod.clib.roi_pool_fwd(bottom, rois, 7, 7, 1 / 16.)
+    assert np.array_equal(top.cpu().numpy(), wt) and np.array_equal(arg.cpu().numpy(), wa)
+
+
+@pytest.mark.parametrize("mode", ["cpu", "gpu"])
+def test_fwd_tiled_sorted_lists_many_images(oracle_mod, mode, monkeypatch):
+    """R > 4096: the tiled kernel takes its per-image RoI lists from the counting-sort
+    pre-pass in the workspace.  Batch indices are shuffled and some are out of range."""
+    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", "tiled")
+    B, H, W, C = 24, 38, 50, 32
+    bottom = syn.feature_map(30, B, H, W, C)
+    rois = np.concatenate([syn.rois_for_pool(31, 5000, B), syn.adversarial_rois(B, W, H)])
+    rng = np.random.default_rng(32)
+    rois = rois[rng.permutation(rois.shape[0])]
+    rois[::97, 0] = B + 3            # no such image: (0, -1)
+    rois[5::211, 0] = -2
+    bad = (rois[:, 0] < 0) | (rois[:, 0] >= B)
+    safe = rois.copy()
+    safe[bad, 0] = 0                 # the oracle would read out of bounds for those rows
+    wt, wa = oracle_mod.clib.roi_pool_fwd(bottom, safe, 7, 7, 1 / 16., bin_mode=0 if mode == "cpu" else 1)
+    top, arg = ops.roi_pool_forward(bottom, rois, 7, 7, 1 / 16., bin_mode=mode)
+    t, a = top.cpu().numpy(), arg.cpu().numpy()
+    assert np.array_equal(a[~bad], wa[~bad]) and np.array_equal(t[~bad], wt[~bad])
+    assert not t[bad].any() and (a[bad] == -1).all()
+    # same answer from the direct kernel and without a workspace
+    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", "direct")
+    t2, a2 = ops.roi_pool_forward(bottom, rois, 7, 7, 1 / 16., bin_mode=mode)
+    assert np.array_equal(t2.cpu().numpy(), t) and np.array_equal(a2.cpu().numpy(), a)
+
+
+@pytest.mark.parametrize("B,R", [(1, 300), (2, 700), (3, 40), (5, 4096), (1, 1)])
+def test_fwd_tiled_chunked_scan_lists(oracle_mod, B, R, monkeypatch):
+    """R <= 4096: RoI lists are built inside each CTA; few images split their RoIs over
+    several CTAs (chunk = RoI index mod nchunks).  Also without argmax."""
+    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", "tiled")
+    H, W, C = 38, 50, 48
+    bottom = syn.feature_map(33, B, H, W, C)
+    rois = syn.rois_for_pool(34, R, B)
+    wt, wa, t, a = _fwd_both(oracle_mod, bottom, rois, 7, 7, 1 / 16., "cpu")
+    assert np.array_equal(t, wt) and np.array_equal(a, wa)
+    t3, a3 = ops.roi_pool_forward(bottom, rois, 7, 7, 1 / 16., need_argmax=False)
+    assert a3 is None and np.array_equal(t3.cpu().numpy(), wt)
+
+
+def test_fwd_workspace_query_and_null_workspace(oracle_mod):
+    """The C ABI accepts a NULL workspace (direct kernel for big batches) and reports the
+    scratch size it wants."""
+    import ctypes
+    from wssdl_bus_b200 import _lib
+    L = _lib.lib()
+    assert L.wssdl_roi_pool_fwd_workspace_bytes(256, 76800) >= 4 * (256 + 2 + 76800)
+    B, H, W, C, R = 4, 20, 24, 16, 5000
+    bottom = syn.feature_map(35, B, H, W, C)
+    rois = syn.rois_for_pool(36, R, B, im_w=W * 16, im_h=H * 16)
+    x = torch.from_numpy(bottom).cuda()
+    r = torch.from_numpy(rois).cuda()
+    top = torch.empty((R, 7, 7, C), device="cuda")
+    arg = torch.empty((R, 7, 7, C), device="cuda", dtype=torch.int32)
+    vp = ctypes.c_void_p
+    rc = L.wssdl_roi_pool_fwd(vp(x.data_ptr()), vp(r.data_ptr()), B, H, W, C, R, 7, 7, 1 / 16., 0,
+                              vp(top.data_ptr()), vp(arg.data_ptr()), None, 0,
+                              vp(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
     wt, wa = oracle_mod.clib.roi_pool_fwd(bottom, rois, 7, 7, 1 / 16.)
     assert np.array_equal(top.cpu().numpy(), wt) and np.array_equal(arg.cpu().numpy(), wa)
 

@@ -24,7 +24,9 @@ _vp, _i, _f, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_d
 SIGNATURES = {
     "wssdl_version": (_i, []),
     "wssdl_error_string": (ctypes.c_char_p, [_i]),
-    "wssdl_roi_pool_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "wssdl_roi_pool_fwd_workspace_bytes": (_sz, [_i, _i]),
+    "wssdl_roi_pool_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _sz,
+                                _vp]),
     "wssdl_roi_pool_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "wssdl_nms_workspace_bytes": (_sz, [_i]),
     "wssdl_nms": (_i, [_vp, _i, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -152,16 +152,30 @@ roi_pool_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
-// Backward, atomic scatter.  One CTA per (roi, ph-slice).  The reference's gather
-// (roi_pooling_op.cc:400-455) adds top_diff[n,ph,pw,c] to bottom_diff[b,h,w,c] iff
-//   b == roi batch, (h,w) inside the rounded RoI (:415-419), ph in [phstart(h),phend(h)),
-//   pw in [pwstart(w),pwend(w)) (:437-445) and argmax[n,ph,pw,c] == (h*W+w)*C+c (:449).
-// The feasible h-interval of every ph and w-interval of every pw are evaluated once per
-// CTA with the reference's own float expressions (they are monotone in h / w, so each
-// set is an interval) and kept in shared memory; the per-element test is then four
-// integer compares.  That makes the scatter equal to the gather for arbitrary argmax
-// input, including malformed RoIs whose forward argmax is valid but whose in-RoI test
-// fails.
+// Forward, shared-memory resident channel slice ("tiled").
+//
+// The direct kernel above re-reads every RoI's cells from L2: with 300 overlapping RoIs on
+// a 38x50 map that is ~35x the map per image (ncu, profiles/r01_roi_pool_fwd_v2: 34 GB of
+// L2->SM reads for 15.4 GB of output, the kernel stalls on long_scoreboard at 57 % of the
+// DRAM peak).  Here one CTA owns (image, 16-channel slice): the slice of the whole map
+// (H*W*64 B = 121.6 KB for 38x50) is staged ONCE into shared memory with cp.async, then
+// every RoI of that image is pooled out of shared memory.  L2 sees the map once per
+// (image, RoI chunk) and otherwise only the output stream, so the kernel is bound by the
+// HBM write stream as the roofline says it should be.
+//   - bins average only ~4.5 cells, so per-bin bookkeeping, not the compare/select work,
+//     is what costs issue slots: a work item is (RoI, pw, 8 channels) and its thread walks
+//     ph = 0..PH-1 down that column of bins, paying the decode once per PH bins;
+//   - two threads per bin column: 32 B of each 64 B cell chunk per thread (2 x LDS.128),
+//     outputs leave as full 32 B sectors (the neighbouring slice CTAs, launched back to
+//     back, complete the 128 B lines in L2 before they are evicted);
+//   - bin edges of a batch of RoIs are computed once per CTA with the reference's float
+//     expressions (roi_cells / bin_lo / bin_hi) and kept packed in shared memory;
+//   - warps draw 32 items at a time from a shared counter (RoI sizes vary widely);
+//   - RoIs are grouped by image either by an in-CTA scan of the batch column (R <=
+//     T_SCAN_MAX_R, no workspace) or by a counting-sort pre-pass (roi_bucket_kernel) into
+//     the caller's workspace.  Bucket B collects RoIs whose batch index is outside [0,B):
+//     they produce (0,-1) without touching the map.
+
 // Exact unsigned division by a runtime constant d >= 1 for n < 2^31 (Granlund-Montgomery
 // round-up magic: l = ceil(log2 d), m = ceil(2^(31+l)/d) < 2^32, q = (n*m) >> (31+l)).
 struct FastDiv {
@@ -179,6 +193,328 @@ __device__ __forceinline__ unsigned fastdiv(unsigned n, FastDiv f) {
   return (unsigned)(((unsigned long long)n * f.mul) >> f.shift);
 }
 
+
+constexpr int T_SLICE = 16;             // channels per CTA
+constexpr int T_LANES = T_SLICE / 4;    // float4 lanes per cell
+constexpr int T_THREADS = 1024;
+constexpr int T_SCAN_MAX_R = 4096;      // in-CTA RoI list capacity (scan mode)
+constexpr int T_MAX_RB = 1024;          // RoIs whose bin edges are resident at a time
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+__device__ __forceinline__ int roi_bucket(float batch, int B) {
+  const int b = (int)batch;             // same conversion as roi_cells()
+  return (b >= 0 && b < B) ? b : B;
+}
+
+// Counting sort of RoI indices by image, one CTA.  img_start[B+2] (exclusive offsets),
+// perm[R] (RoI indices grouped by bucket).  Dynamic smem: (B+1) counters + R uint16
+// bucket ids when they fit (cache16 != 0).
+__global__ void __launch_bounds__(1024)
+roi_bucket_kernel(const float* __restrict__ rois, int R, int B, int cache16,
+                  int* __restrict__ img_start, int* __restrict__ perm) {
+  extern __shared__ int s_cnt[];                                   // [B+1]
+  unsigned short* s_b16 = reinterpret_cast<unsigned short*>(s_cnt + (B + 1));
+  __shared__ int s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i <= B; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < R; r0 += 4 * blockDim.x) {
+    int b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * blockDim.x + tid;
+      b[u] = (r < R) ? roi_bucket(__ldg(rois + (size_t)r * 5), B) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * blockDim.x + tid;
+      if (b[u] >= 0) {
+        atomicAdd(&s_cnt[b[u]], 1);
+        if (cache16) s_b16[r] = (unsigned short)b[u];
+      }
+    }
+  }
+  __syncthreads();
+  // exclusive scan of s_cnt[0..B] -> img_start, s_cnt becomes the scatter cursor
+  int carry = 0;
+  for (int i0 = 0; i0 <= B; i0 += blockDim.x) {
+    const int i = i0 + tid;
+    const int v = (i <= B) ? s_cnt[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int k = 0; k < 32; ++k) {
+      const int t = s_warp[k];
+      if (k < warp) woff += t;
+      total += t;
+    }
+    const int excl = carry + woff + x - v;
+    if (i <= B) { s_cnt[i] = excl; img_start[i] = excl; }
+    carry += total;
+    __syncthreads();
+  }
+  if (tid == 0) img_start[B + 1] = carry;   // == R
+  for (int r = tid; r < R; r += blockDim.x) {
+    const int b = cache16 ? (int)s_b16[r] : roi_bucket(__ldg(rois + (size_t)r * 5), B);
+    perm[atomicAdd(&s_cnt[b], 1)] = r;
+  }
+}
+
+// First-maximum update with the two conditional moves on the FMA pipe.  FSETP, FSEL and SEL
+// all issue to the half-rate ALU pipe (16 lanes/clk per scheduler), which is what bounded
+// the tiled kernel (ncu: math_pipe_throttle, ALU 70 %, FMA 20 %).  `@p FMUL m, v, 1.0f` and
+// `@p IMAD mi, cell, 1, 0` are exact, run on the full-rate FP32 pipe / the FMA-heavy pipe,
+// and leave one ALU instruction (the compare) per element.  `one_f` / `one_i` come from
+// kernel parameters so ptxas cannot fold the multiplications back into selects; the eight
+// channels of a thread use eight distinct integer ones, otherwise ptxas merges their
+// common cell*1 product and falls back to SEL.
+struct Ones {
+  float f;
+  int i[8];
+};
+__device__ __forceinline__ void upd_fma(float v, int cell, float& m, int& mi, float one_f,
+                                        int one_i) {
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.gt.f32 p, %2, %0;\n\t"            // strict '>' (cc:187): NaN never wins
+      "@p mul.rn.f32 %0, %2, %4;\n\t"
+      "@p mad.lo.s32 %1, %3, %5, 0;\n\t}"
+      : "+f"(m), "+r"(mi)
+      : "f"(v), "r"(cell), "f"(one_f), "r"(one_i));
+}
+
+// 256-bit global stores (sm_100a: STG.E.256): one lane writes 8 consecutive channels, the
+// two lanes of a bin column fill a 64 B half line in one LSU wavefront.
+template <bool STREAM_ST>
+__device__ __forceinline__ void st256(float* p, const float4 a, const float4 b) {
+  if (STREAM_ST)
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x),
+                 "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+  else
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x),
+                 "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+template <bool STREAM_ST>
+__device__ __forceinline__ void st256(int* p, const int4 a, const int4 b) {
+  if (STREAM_ST)
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x),
+                 "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+  else
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x),
+                 "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
+// dynamic shared memory a CTA may ask for: 227 KB minus the kernels' static arrays
+constexpr int T_DYN_SMEM_MAX = 227 * 1024 - 1024;
+constexpr int T_CLASSES = 64;           // RoI cost classes: min(rows/bin,7)*8 + min(cells/row,7)
+
+template <int BIN_MODE, bool STREAM_ST>
+__global__ void __launch_bounds__(T_THREADS, 1)
+roi_pool_fwd_tiled_kernel(const float* __restrict__ bottom, const float* __restrict__ rois,
+                          const int* __restrict__ perm, const int* __restrict__ img_start,
+                          int B, int H, int W, int C, int R, int PH, int PW,
+                          float spatial_scale, int RB, FastDiv divPW, const Ones ones,
+                          float* __restrict__ top, int* __restrict__ argmax) {
+  extern __shared__ __align__(16) unsigned char t_smem[];
+  __shared__ int s_count, s_next;
+  __shared__ int s_hist[T_CLASSES], s_start[T_CLASSES];
+  const int tid = threadIdx.x;
+  const int slice = blockIdx.x, chunk = blockIdx.y, nchunks = gridDim.y;
+  const int img = blockIdx.z;                       // == B: RoIs with no valid image
+  float4* s_map = reinterpret_cast<float4*>(t_smem);
+  unsigned* s_he = reinterpret_cast<unsigned*>(s_map + (size_t)H * W * T_LANES);  // hs | he<<16
+  unsigned* s_we = s_he + RB * PH;                                                // ws | we<<16
+  int* s_n = reinterpret_cast<int*>(s_we + RB * PW);     // RoI index in the caller's array
+  int* s_cls = s_n + RB;                                 // cost class
+  int* s_order = s_cls + RB;                             // resident RoIs, heaviest class first
+  int* s_list = s_order + RB;                            // scan mode only
+
+  // ---- this CTA's RoIs
+  const int* list;
+  int r_begin, r_end;
+  if (perm != nullptr) {
+    const int a = img_start[img];
+    const int n_img = img_start[img + 1] - a;
+    list = perm + a;
+    r_begin = (int)((long long)n_img * chunk / nchunks);
+    r_end = (int)((long long)n_img * (chunk + 1) / nchunks);
+  } else {
+    // the chunk of a RoI is a function of its index alone, so every slice CTA of this
+    // (image, chunk) collects the same set whatever order the atomics resolve in
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int r = tid; r < R; r += blockDim.x)
+      if (r % nchunks == chunk && roi_bucket(__ldg(rois + (size_t)r * 5), B) == img)
+        s_list[atomicAdd(&s_count, 1)] = r;
+    __syncthreads();
+    list = s_list;
+    r_begin = 0;
+    r_end = s_count;
+  }
+  if (r_end <= r_begin) return;
+
+  // ---- stage the channel slice of the whole map (asynchronously; the first batch of bin
+  // edges is computed while it lands)
+  const bool valid_img = img < B;
+  if (valid_img) {
+    const int CV = C >> 2;
+    const float4* src = reinterpret_cast<const float4*>(bottom + (size_t)img * H * W * C) +
+                        slice * T_LANES;
+    const int n4 = H * W * T_LANES;
+    for (int i = tid; i < n4; i += blockDim.x)
+      cp_async16(s_map + i, src + (size_t)(i >> 2) * CV + (i & 3));
+  }
+  bool staged = false;
+
+  const int lane32 = tid & 31;
+  const int WC = W * C;
+  const size_t ph_stride = (size_t)PW * C;          // output elements between ph and ph+1
+
+  for (int r0 = r_begin; r0 < r_end; r0 += RB) {
+    const int nb = min(RB, r_end - r0);
+    __syncthreads();                                // previous batch fully consumed
+    if (tid == 0) s_next = 0;
+    if (tid < T_CLASSES) s_hist[tid] = 0;
+    __syncthreads();
+    for (int rl = tid; rl < nb; rl += blockDim.x) {
+      const int n = list[r0 + rl];
+      s_n[rl] = n;
+      const RoiCells g = roi_cells(rois + (size_t)n * 5, spatial_scale, PH, PW);
+      int max_nh = 0, max_nw = 0;
+      for (int ph = 0; ph < PH; ++ph) {
+        int hs = min(max(bin_lo<BIN_MODE>(ph, g.bin_h) + g.start_h, 0), H);   // cc:167-176
+        int he = min(max(bin_hi<BIN_MODE>(ph, g.bin_h) + g.start_h, 0), H);
+        if (!valid_img) hs = he = 0;
+        s_he[rl * PH + ph] = (unsigned)hs | ((unsigned)he << 16);
+        max_nh = max(max_nh, he - hs);
+      }
+      for (int pw = 0; pw < PW; ++pw) {
+        int ws = min(max(bin_lo<BIN_MODE>(pw, g.bin_w) + g.start_w, 0), W);
+        int we = min(max(bin_hi<BIN_MODE>(pw, g.bin_w) + g.start_w, 0), W);
+        if (!valid_img) ws = we = 0;
+        s_we[rl * PW + pw] = (unsigned)ws | ((unsigned)we << 16);
+        max_nw = max(max_nw, we - ws);
+      }
+      // cost class: lanes of a warp run in lock step over ph, so RoIs that share a warp
+      // should have the same rows-per-bin and cells-per-row
+      const int cls = min(max_nh, 7) * 8 + min(max_nw, 7);
+      s_cls[rl] = cls;
+      atomicAdd(&s_hist[cls], 1);
+    }
+    if (!staged) { cp_async_wait_all(); staged = true; }
+    __syncthreads();
+    // counting sort by class, heaviest first (they are handed out first)
+    if (tid < T_CLASSES) {
+      int before = 0;
+      for (int k = tid + 1; k < T_CLASSES; ++k) before += s_hist[k];
+      s_start[tid] = before;
+    }
+    __syncthreads();
+    for (int rl = tid; rl < nb; rl += blockDim.x) s_order[atomicAdd(&s_start[s_cls[rl]], 1)] = rl;
+    __syncthreads();
+
+    // One work item = (RoI, pw, 8-channel half of the slice): the thread walks ph = 0..PH-1
+    // down its column, so the item decode is paid once per PH bins.  Warps draw 32 items
+    // at a time from a shared counter.
+    const int items = nb * PW * 2;
+    for (;;) {
+      int base = 0;
+      if (lane32 == 0) base = atomicAdd(&s_next, 32);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= items) break;
+      const int it = base + lane32;
+      if (it >= items) continue;
+      const int half = it & 1;            // channels [8*half, 8*half+8) of the slice
+      const int col = it >> 1;
+      const int rs = (int)fastdiv((unsigned)col, divPW);
+      const int pw = col - rs * PW;
+      const int rl = s_order[rs];
+      const unsigned ww = s_we[rl * PW + pw];
+      const int ws = ww & 0xffff, nw = (int)(ww >> 16) - ws;
+      // The 4 bin columns of a quarter warp mostly sit an even number of cells apart, i.e.
+      // in the same 16 banks.  Odd columns therefore read their two 16 B chunks in swapped
+      // order (2.3 -> 1.5 wavefronts per LDS.128 on proposal RoIs); registers m[0..3] then
+      // hold the UPPER four channels and the roles are swapped back at the store.
+      const int sw = col & 1;
+      const int c = slice * T_SLICE + half * 8;
+      const int c_a = c + 4 * sw, c_b = c + 4 * (1 - sw);   // channels of m[0..3] / m[4..7]
+      const unsigned* he_p = s_he + rl * PH;
+      size_t o = ((size_t)s_n[rl] * PH * PW + pw) * C + c;
+      const float4* pcol = s_map + ws * T_LANES + half * 2;
+      const int off_a = sw, off_b = 1 - sw;
+      const int cellW = ws * C;
+#pragma unroll 1
+      for (int ph = 0; ph < PH; ++ph, o += ph_stride) {
+        const unsigned hh = he_p[ph];
+        const int hs = hh & 0xffff, nh = (int)(hh >> 16) - hs;
+        const bool is_empty = (nh <= 0) || (nw <= 0);
+        float m[8];
+        int mi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {               // cc:180-182
+          m[k] = is_empty ? 0.f : -FLT_MAX;
+          mi[k] = -1 - (k < 4 ? c_a + k : c_b + k - 4);   // + channel at the end => -1 if never updated
+        }
+        if (!is_empty) {
+          const float4* prow = pcol + hs * W * T_LANES;
+          int cellC0 = hs * WC + cellW;
+#pragma unroll 1
+          for (int r = nh; r > 0; --r, prow += W * T_LANES, cellC0 += WC) {
+            const float4* p = prow;
+            int cellC = cellC0;
+#define WSSDL_UPD8(VA, VB, CELL)                                  \
+  do {                                                            \
+    upd_fma(VA.x, CELL, m[0], mi[0], ones.f, ones.i[0]);          \
+    upd_fma(VA.y, CELL, m[1], mi[1], ones.f, ones.i[1]);          \
+    upd_fma(VA.z, CELL, m[2], mi[2], ones.f, ones.i[2]);          \
+    upd_fma(VA.w, CELL, m[3], mi[3], ones.f, ones.i[3]);          \
+    upd_fma(VB.x, CELL, m[4], mi[4], ones.f, ones.i[4]);          \
+    upd_fma(VB.y, CELL, m[5], mi[5], ones.f, ones.i[5]);          \
+    upd_fma(VB.z, CELL, m[6], mi[6], ones.f, ones.i[6]);          \
+    upd_fma(VB.w, CELL, m[7], mi[7], ones.f, ones.i[7]);          \
+  } while (0)
+#pragma unroll 1   // bins are 1-3 cells wide: unrolling only adds branches (measured)
+            for (int left = nw; left > 0; --left, p += T_LANES, cellC += C) {
+              const float4 v0 = p[off_a], v1 = p[off_b];
+              WSSDL_UPD8(v0, v1, cellC);
+            }
+#undef WSSDL_UPD8
+          }
+        }
+        const float4 ta = make_float4(m[0], m[1], m[2], m[3]);
+        const float4 tb = make_float4(m[4], m[5], m[6], m[7]);
+        const int4 aa = make_int4(mi[0] + c_a, mi[1] + c_a + 1, mi[2] + c_a + 2, mi[3] + c_a + 3);
+        const int4 ab = make_int4(mi[4] + c_b, mi[5] + c_b + 1, mi[6] + c_b + 2, mi[7] + c_b + 3);
+        st256<STREAM_ST>(top + o, sw ? tb : ta, sw ? ta : tb);
+        if (argmax != nullptr) st256<STREAM_ST>(argmax + o, sw ? ab : aa, sw ? aa : ab);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Backward, atomic scatter.  One CTA per (roi, ph-slice).  The reference's gather
+// (roi_pooling_op.cc:400-455) adds top_diff[n,ph,pw,c] to bottom_diff[b,h,w,c] iff
+//   b == roi batch, (h,w) inside the rounded RoI (:415-419), ph in [phstart(h),phend(h)),
+//   pw in [pwstart(w),pwend(w)) (:437-445) and argmax[n,ph,pw,c] == (h*W+w)*C+c (:449).
+// The feasible h-interval of every ph and w-interval of every pw are evaluated once per
+// CTA with the reference's own float expressions (they are monotone in h / w, so each
+// set is an interval) and kept in shared memory; the per-element test is then four
+// integer compares.  That makes the scatter equal to the gather for arbitrary argmax
+// input, including malformed RoIs whose forward argmax is valid but whose in-RoI test
+// fails.
 template <int VEC>
 __global__ void __launch_bounds__(256)
 roi_pool_bwd_atomic_kernel(const float* __restrict__ top_diff, const int* __restrict__ argmax,
@@ -383,10 +719,79 @@ int pick_block_x(int CV) {
 
 }  // namespace
 
+namespace {
+
+// Shape test + launch geometry of the tiled forward kernel.
+struct TiledPlan {
+  bool ok;
+  bool scan;          // RoI lists built in-CTA (no workspace)
+  int RB, nchunks;
+  size_t smem;
+};
+
+size_t tiled_workspace_bytes(int B, int R) {
+  return sizeof(int) * ((size_t)B + 2 + (size_t)R) + 16;
+}
+
+TiledPlan plan_tiled(int B, int H, int W, int C, int R, int PH, int PW, bool vec4,
+                     size_t workspace_bytes) {
+  TiledPlan p = {false, false, 0, 1, 0};
+  if (!vec4 || C % T_SLICE != 0 || H > 65535 || W > 65535 || B + 1 > 65535) return p;
+  if (PH <= 0 || PW <= 0) return p;
+  p.scan = R <= T_SCAN_MAX_R;
+  if (!p.scan && workspace_bytes < tiled_workspace_bytes(B, R)) return p;
+  if (!p.scan && (size_t)(B + 1) * sizeof(int) > (size_t)T_DYN_SMEM_MAX) return p;   // bucket counters
+  const size_t map_bytes = (size_t)H * W * T_SLICE * sizeof(float);
+  const size_t list_bytes = p.scan ? sizeof(int) * (size_t)T_SCAN_MAX_R : 0;
+  const size_t budget = T_DYN_SMEM_MAX;
+  if (map_bytes + list_bytes >= budget) return p;
+  // per resident RoI: PH + PW packed edges, its index, cost class and sorted position
+  const size_t per_roi = sizeof(int) * ((size_t)PH + PW + 3);
+  const size_t rb = (budget - map_bytes - list_bytes) / per_roi;
+  if (rb < 16) return p;
+  p.RB = (int)(rb < (size_t)T_MAX_RB ? rb : (size_t)T_MAX_RB);
+  // no point keeping more RoIs resident than a CTA will ever see
+  if (p.RB > R) p.RB = R < 16 ? 16 : R;          // an image may own every RoI
+  p.smem = map_bytes + list_bytes + per_roi * p.RB;
+  // split an image's RoIs over CTAs only while the grid stays inside one wave and a chunk
+  // still amortises staging the slice (>= 16 RoIs)
+  const long long base = (long long)(C / T_SLICE) * (B > 0 ? B : 1);
+  const int avg = R / (B > 0 ? B : 1);
+  while (base * p.nchunks * 2 <= WSSDL_NUM_SMS && avg / (p.nchunks * 2) >= 16) p.nchunks *= 2;
+  p.ok = true;
+  return p;
+}
+
+// Opt a kernel into 227 KB of dynamic shared memory once per device (the attribute is
+// per device; one process may drive several).
+template <typename K>
+cudaError_t allow_big_smem(K kernel, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_DYN_SMEM_MAX);
+  if (e == cudaSuccess) __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+  return e;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+}  // namespace
+
+extern "C" size_t wssdl_roi_pool_fwd_workspace_bytes(int B, int R) {
+  if (B < 0 || R < 0) return 0;
+  return tiled_workspace_bytes(B, R);
+}
+
 extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B, int H, int W,
                                   int C, int R, int PH, int PW, float spatial_scale,
-                                  int bin_mode, float* top, int* argmax,
-                                  wssdl_stream_t stream) {
+                                  int bin_mode, float* top, int* argmax, void* workspace,
+                                  size_t workspace_bytes, wssdl_stream_t stream) {
   // attribute checks of the op (roi_pooling_op.cc:73-82) plus pointer sanity
   if (B < 0 || H < 0 || W < 0 || C < 0 || R < 0 || PH < 0 || PW < 0) return WSSDL_EINVAL;
   if (bin_mode != WSSDL_BIN_CPU_TRUNC && bin_mode != WSSDL_BIN_GPU_CEIL) return WSSDL_EINVAL;
@@ -396,17 +801,73 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
   if ((long long)H * W * C >= (1ll << 31) || (long long)R * PH >= (1ll << 31)) return WSSDL_ELIMIT;
   const bool vec4 = (C % 4 == 0) && aligned16(bottom) && aligned16(top) &&
                     (argmax == nullptr || aligned16(argmax));
+  cudaStream_t s = to_cuda(stream);
+
+  // Kernel choice.  The tiled kernel wins whenever RoIs of an image overlap enough for the
+  // map to be re-read several times (the detector's case: hundreds of RoIs per image on a
+  // map of a few thousand cells); experiments: WSSDL_ROI_FWD_KERNEL=direct|tiled,
+  // WSSDL_ROI_FWD_STREAM_ST=0|1.
+  // (read per call so tests can force either kernel)
+  const char* kenv = getenv("WSSDL_ROI_FWD_KERNEL");
+  const int kernel_env = !kenv ? 0 : (kenv[0] == 'd' ? 1 : (kenv[0] == 't' ? 2 : 0));
+  const int stream_st = env_int("WSSDL_ROI_FWD_STREAM_ST", 1);
+  if (workspace == nullptr) workspace_bytes = 0;
+  // the tiled kernel stores 256 bits per lane: outputs must be 32-byte aligned
+  const bool al32 = ((reinterpret_cast<uintptr_t>(top) | reinterpret_cast<uintptr_t>(argmax)) & 31u) == 0;
+  const TiledPlan tp = plan_tiled(B, H, W, C, R, PH, PW, vec4 && al32, workspace_bytes);
+  // Measured on B200 (profiles/r01_roi_fwd_direct_vs_tiled.txt): the tiled kernel wins for
+  // one or two images (C1/C2: the direct kernel cannot fill the machine with latency-bound
+  // L2 reads), ties at 256 images (3.63 vs 3.57 ms: LSU wavefronts / issue slots vs the L2
+  // throughput cap) and loses when bins are large (C3, 14x14 on 1024 channels).  Default:
+  // tiled while its grid fits one wave.
+  const bool tiled_pays = tp.scan && (long long)(C / T_SLICE) * B * tp.nchunks <= WSSDL_NUM_SMS &&
+                          PH * PW <= 64 && (long long)R * PH * PW * 2 >= (long long)B * H * W;
+  if (tp.ok && kernel_env != 1 && (tiled_pays || kernel_env == 2)) {
+    int* img_start = nullptr;
+    int* perm = nullptr;
+    if (!tp.scan) {
+      img_start = static_cast<int*>(workspace);
+      perm = img_start + (B + 2);
+      const int cache16 = ((size_t)(B + 1) * 4 + (size_t)R * 2 <= (size_t)T_DYN_SMEM_MAX) ? 1 : 0;
+      const size_t bsmem = (size_t)(B + 1) * 4 + (cache16 ? (size_t)R * 2 : 0);
+      static unsigned long long done_b = 0;
+      WSSDL_RETURN_IF_CUDA(allow_big_smem(roi_bucket_kernel, &done_b));
+      roi_bucket_kernel<<<1, 1024, bsmem, s>>>(rois, R, B, cache16, img_start, perm);
+      WSSDL_CHECK_LAUNCH();
+    }
+    const FastDiv dPW = make_fastdiv((unsigned)PW);
+    const Ones ones = {1.0f, {1, 1, 1, 1, 1, 1, 1, 1}};
+    dim3 grid((unsigned)(C / T_SLICE), (unsigned)tp.nchunks, (unsigned)(B + 1));
+#define LAUNCH_TILED(M, ST)                                                                    \
+  do {                                                                                         \
+    static unsigned long long done_t = 0;                                                      \
+    WSSDL_RETURN_IF_CUDA(allow_big_smem(roi_pool_fwd_tiled_kernel<M, ST>, &done_t));           \
+    roi_pool_fwd_tiled_kernel<M, ST><<<grid, T_THREADS, tp.smem, s>>>(                         \
+        bottom, rois, perm, img_start, B, H, W, C, R, PH, PW, spatial_scale, tp.RB, dPW, ones,  \
+        top, argmax);                                                                          \
+  } while (0)
+    if (bin_mode == WSSDL_BIN_CPU_TRUNC) {
+      if (stream_st) LAUNCH_TILED(WSSDL_BIN_CPU_TRUNC, true);
+      else LAUNCH_TILED(WSSDL_BIN_CPU_TRUNC, false);
+    } else {
+      if (stream_st) LAUNCH_TILED(WSSDL_BIN_GPU_CEIL, true);
+      else LAUNCH_TILED(WSSDL_BIN_GPU_CEIL, false);
+    }
+#undef LAUNCH_TILED
+    WSSDL_CHECK_LAUNCH();
+    return WSSDL_OK;
+  }
+
   const int CV = vec4 ? C / 4 : C;
   // channel vectors per thread: 2 when the channel count allows it (tuning knob for
   // experiments: WSSDL_ROI_FWD_VPT=1|2)
-  static const int vpt_env = [] { const char* e = getenv("WSSDL_ROI_FWD_VPT"); return e ? atoi(e) : 0; }();
+  const int vpt_env = env_int("WSSDL_ROI_FWD_VPT", 0);
   int vpt = (vec4 && CV % 64 == 0) ? 2 : 1;
   if (vpt_env == 1) vpt = 1;
   const int lanes = CV / vpt;
   dim3 block(pick_block_x(lanes), 1);
   block.y = max(1, min(PW, 128 / (int)block.x));
   dim3 grid((unsigned)(R * PH), (unsigned)ceil_div(lanes, block.x));
-  cudaStream_t s = to_cuda(stream);
 #define LAUNCH_FWD(V, M, CVT, VPT)                                                            \
   roi_pool_fwd_kernel<V, M, CVT, VPT><<<grid, block, 0, s>>>(bottom, rois, B, H, W, C, PH, PW, \
                                                              spatial_scale, top, argmax)
