@@ -167,6 +167,18 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, images):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+    (profiles/roofline_traffic.json), only when it was taken on the same batch size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[kernel]
+        if int(t["images"]) == int(images):
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), t["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -266,19 +278,25 @@ def run_ours(args):
         value = world * B / (ms_step / 1e3)
         peak, peak_src = measured_peak()
         achieved = B * ROI_POOL_FWD_BYTES_PER_IMAGE / (roi_ms / 1e3) / 1e9
+        tiled = os.environ.get("WSSDL_ROI_FWD_KERNEL", "").startswith("t")
+        kname = "roi_pool_fwd_tiled_kernel" if tiled else "roi_pool_fwd_kernel"
+        traffic, traffic_src = measured_traffic(kname, B)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": max(Wm, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(B, world),
-            "roofline": {"kernel": "roi_pool_fwd_kernel<4,CPU_TRUNC>", "bound": "hbm",
+            "roofline": {"kernel": kname + ("<CPU_TRUNC>" if tiled else "<4,CPU_TRUNC,128,2>"),
+                         "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": B * ROI_POOL_FWD_BYTES_PER_IMAGE,
                          "ms_per_launch": roi_ms},
             "kernels_ms_per_step": {"proposals_kernel": prop_ms, "roi_pool_fwd_kernel": roi_ms},
-            "gpu_launches": 2 * K,
+            # proposals_kernel + roi_pool_fwd kernel (+ roi_bucket_kernel when the tiled
+            # kernel sorts RoIs by image) per step
+            "gpu_launches": (3 if tiled else 2) * K,
             "clocks": clocks,
             "rois_per_image": [int(counts.min()), int(counts.max())],
         }

@@ -18,7 +18,7 @@ def test_iou_golden_bit_exact(golden):
 
 
 @pytest.mark.parametrize("N,K", [(0, 5), (5, 0), (1, 1), (17100, 20), (5944, 3), (2020, 20),
-                                 (10000, 1024), (3000, 1500)])
+                                 (10000, 1024), (3000, 1500), (777, 1023), (64, 65), (70, 4)])
 def test_iou_vs_oracle_bit_exact(oracle_mod, N, K):
     b = syn.random_boxes(400 + N, N).astype(np.float64)
     q = syn.random_boxes(401 + K, K, lo=30, hi=300).astype(np.float64)

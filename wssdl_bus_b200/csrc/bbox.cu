@@ -7,9 +7,8 @@
 //   wssdl_bbox_transform         : fast_rcnn/bbox_transform.py:10-28
 //
 // All of these are elementwise / outer-product kernels bound by the output stream
-// (N*K*8 B for the fp64 IoU matrix).  One thread per output element, k fastest, so stores
-// are fully coalesced; the query boxes (K*32 B) are staged in shared memory per CTA when
-// they fit, the row box is a broadcast load.  Every arithmetic operation is written with
+// (N*K*8 B for the fp64 IoU matrix); see the tiling note above bbox_overlaps_kernel.
+// Every arithmetic operation is written with
 // the round-to-nearest intrinsics so the compiler cannot contract mul+add into FMA: the
 // reference's expression tree (bbox.c:2068: ((bw*bh)+qarea)-(iw*ih), then (iw*ih)/ua) is
 // evaluated with exactly one rounding per operation, which makes the fp64 path bit-exact.
@@ -31,60 +30,85 @@ template <> struct Ops<float> {
   static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
 };
 
-template <typename T> struct Box { T x1, y1, x2, y2; };
-
 // Cython lowers min(a,b)/max(a,b) on C doubles to (b < a ? b : a) / (b > a ? b : a)
 template <typename T> __device__ __forceinline__ T cmin(T a, T b) { return b < a ? b : a; }
 template <typename T> __device__ __forceinline__ T cmax(T a, T b) { return b > a ? b : a; }
 
+// Output-stream bound for large matrices (N*K*sizeof(T) written once, the boxes are
+// noise), so the kernel is organised around the store: a CTA owns a tile of OV_ROWS rows x
+// (KX * VEC) columns, a thread owns VEC consecutive columns (one 16-byte store per row) and
+// walks down the rows of the tile.  Its VEC query boxes and their areas live in registers
+// for the whole tile; the tile's row boxes and areas are staged once in shared memory and
+// read as broadcasts.  No integer division, no recomputed areas, one vector store per VEC
+// results.  The block shape adapts to K (KX = pow2 >= K/VEC, capped at OV_THREADS) so the
+// detector's skinny matrices (17100 x 20) still fill their warps.
+constexpr int OV_THREADS = 256;
+constexpr int OV_ROWS = 64;       // rows per CTA tile
+
+template <typename T> struct BoxA { T x1, y1, x2, y2, area; };
+
 template <typename T, int KIND>
-__device__ __forceinline__ T overlap(const Box<T>& b, const Box<T>& q) {
+__device__ __forceinline__ T overlap_a(const BoxA<T>& b, const BoxA<T>& q) {
   using O = Ops<T>;
   const T one = (T)1;
-  const T iw = O::add(O::sub(cmin(b.x2, q.x2), cmax(b.x1, q.x1)), one);
-  if (!(iw > (T)0)) return (T)0;
-  const T ih = O::add(O::sub(cmin(b.y2, q.y2), cmax(b.y1, q.y1)), one);
-  if (!(ih > (T)0)) return (T)0;
-  const T barea = O::mul(O::add(O::sub(b.x2, b.x1), one), O::add(O::sub(b.y2, b.y1), one));
+  const T iw = O::add(O::sub(cmin(b.x2, q.x2), cmax(b.x1, q.x1)), one);     // bbox.pyx:38-41
+  const T ih = O::add(O::sub(cmin(b.y2, q.y2), cmax(b.y1, q.y1)), one);     // :43-46
+  if (!(iw > (T)0) || !(ih > (T)0)) return (T)0;
   const T inter = O::mul(iw, ih);
-  if (KIND == WSSDL_IOU_UI) return O::div(inter, barea);                  // bbox_ui.pyx:45
-  const T qarea = O::mul(O::add(O::sub(q.x2, q.x1), one), O::add(O::sub(q.y2, q.y1), one));
-  const T ua = O::sub(O::add(barea, qarea), inter);                       // bbox.pyx:49-53
+  if (KIND == WSSDL_IOU_UI) return O::div(inter, b.area);                   // bbox_ui.pyx:45
+  const T ua = O::sub(O::add(b.area, q.area), inter);                       // bbox.pyx:49-53
   return O::div(inter, ua);
 }
 
-constexpr int OV_THREADS = 256;
-constexpr int OV_PER_THREAD = 4;
-constexpr int OV_SMEM_K = 1024;   // query boxes staged in shared memory when K <= this
+template <typename T>
+__device__ __forceinline__ BoxA<T> load_box(const T* __restrict__ p) {
+  using O = Ops<T>;
+  BoxA<T> b;
+  b.x1 = p[0]; b.y1 = p[1]; b.x2 = p[2]; b.y2 = p[3];
+  b.area = O::mul(O::add(O::sub(b.x2, b.x1), (T)1), O::add(O::sub(b.y2, b.y1), (T)1));
+  return b;
+}
 
-template <typename T, int KIND>
+template <typename T, int VEC> struct OutVec;
+template <> struct OutVec<float, 4> { using V = float4; };
+template <> struct OutVec<double, 2> { using V = double2; };
+template <> struct OutVec<float, 1> { using V = float; };
+template <> struct OutVec<double, 1> { using V = double; };
+
+template <typename T, int KIND, int VEC>
 __global__ void __launch_bounds__(OV_THREADS)
-bbox_overlaps_kernel(const T* __restrict__ boxes, long long N, const T* __restrict__ query,
-                     int K, T* __restrict__ out) {
-  __shared__ Box<T> s_q[OV_SMEM_K];
-  const bool staged = K <= OV_SMEM_K;
-  if (staged) {
-    for (int k = threadIdx.x; k < K; k += OV_THREADS) {
-      Box<T> q;
-      q.x1 = query[4 * k]; q.y1 = query[4 * k + 1]; q.x2 = query[4 * k + 2]; q.y2 = query[4 * k + 3];
-      s_q[k] = q;
-    }
-    __syncthreads();
-  }
-  const long long total = N * K;
-  const long long base = ((long long)blockIdx.x * OV_PER_THREAD) * OV_THREADS + threadIdx.x;
+bbox_overlaps_kernel(const T* __restrict__ boxes, int N, const T* __restrict__ query, int K,
+                     int kx_log2, T* __restrict__ out) {
+  __shared__ BoxA<T> s_b[OV_ROWS];
+  const int KX = 1 << kx_log2;                  // threads along k
+  const int RY = OV_THREADS >> kx_log2;         // rows in flight per CTA
+  const int tx = threadIdx.x & (KX - 1), ty = threadIdx.x >> kx_log2;
+  const int n0 = blockIdx.y * OV_ROWS;
+  const int rows = min(OV_ROWS, N - n0);
+  for (int r = threadIdx.x; r < rows; r += OV_THREADS) s_b[r] = load_box(boxes + 4 * (size_t)(n0 + r));
+  const int k0 = (blockIdx.x * KX + tx) * VEC;
+  BoxA<T> q[VEC];
 #pragma unroll
-  for (int u = 0; u < OV_PER_THREAD; ++u) {
-    const long long idx = base + (long long)u * OV_THREADS;
-    if (idx >= total) break;
-    const long long n = idx / K;
-    const int k = (int)(idx - n * K);
-    Box<T> b;
-    b.x1 = boxes[4 * n]; b.y1 = boxes[4 * n + 1]; b.x2 = boxes[4 * n + 2]; b.y2 = boxes[4 * n + 3];
-    Box<T> q;
-    if (staged) q = s_q[k];
-    else { q.x1 = query[4 * k]; q.y1 = query[4 * k + 1]; q.x2 = query[4 * k + 2]; q.y2 = query[4 * k + 3]; }
-    out[idx] = overlap<T, KIND>(b, q);
+  for (int v = 0; v < VEC; ++v)
+    if (k0 + v < K) q[v] = load_box(query + 4 * (size_t)(k0 + v));
+  __syncthreads();
+  if (k0 >= K) return;
+  T* orow = out + (size_t)(n0 + ty) * K + k0;
+  const size_t ostep = (size_t)RY * K;
+  for (int r = ty; r < rows; r += RY, orow += ostep) {
+    const BoxA<T> b = s_b[r];
+    T o[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) o[v] = overlap_a<T, KIND>(b, q[v]);
+    if constexpr (VEC == 1) {
+      __stcs(orow, o[0]);
+    } else {
+      using V = typename OutVec<T, VEC>::V;      // K % VEC == 0 on this path: aligned, in range
+      V ov;
+      if constexpr (VEC == 4) ov = make_float4(o[0], o[1], o[2], o[3]);
+      else ov = make_double2(o[0], o[1]);
+      __stcs(reinterpret_cast<V*>(orow), ov);
+    }
   }
 }
 
@@ -95,13 +119,24 @@ int launch_overlaps(const T* boxes, int N, const T* query, int K, int kind, T* o
   const long long total = (long long)N * K;
   if (total == 0) return WSSDL_OK;
   if (!boxes || !query || !out) return WSSDL_EINVAL;
-  const long long per_cta = (long long)OV_THREADS * OV_PER_THREAD;
-  const long long ctas = (total + per_cta - 1) / per_cta;
-  if (ctas > 0x7fffffffll) return WSSDL_ELIMIT;
-  if (kind == WSSDL_IOU)
-    bbox_overlaps_kernel<T, WSSDL_IOU><<<(unsigned)ctas, OV_THREADS, 0, s>>>(boxes, N, query, K, out);
-  else
-    bbox_overlaps_kernel<T, WSSDL_IOU_UI><<<(unsigned)ctas, OV_THREADS, 0, s>>>(boxes, N, query, K, out);
+  constexpr int VECMAX = 16 / (int)sizeof(T);
+  const bool vec = (K % VECMAX == 0) && aligned16(out);
+  const int V = vec ? VECMAX : 1;
+  const int kthreads = (K + V - 1) / V;
+  int kx_log2 = 0;
+  while ((1 << kx_log2) < kthreads && (1 << kx_log2) < OV_THREADS) ++kx_log2;
+  const long long gx = (kthreads + (1 << kx_log2) - 1) >> kx_log2;
+  const long long gy = ((long long)N + OV_ROWS - 1) / OV_ROWS;
+  if (gx > 0x7fffffffll || gy > 65535) {
+    // more than 4.19 M rows: fold the row tiles over grid.x of several launches
+    return WSSDL_ELIMIT;
+  }
+  dim3 grid((unsigned)gx, (unsigned)gy);
+#define LAUNCH_OV(KIND_, V_)                                                                  \
+  bbox_overlaps_kernel<T, KIND_, V_><<<grid, OV_THREADS, 0, s>>>(boxes, N, query, K, kx_log2, out)
+  if (kind == WSSDL_IOU) { if (vec) LAUNCH_OV(WSSDL_IOU, VECMAX); else LAUNCH_OV(WSSDL_IOU, 1); }
+  else { if (vec) LAUNCH_OV(WSSDL_IOU_UI, VECMAX); else LAUNCH_OV(WSSDL_IOU_UI, 1); }
+#undef LAUNCH_OV
   WSSDL_CHECK_LAUNCH();
   return WSSDL_OK;
 }

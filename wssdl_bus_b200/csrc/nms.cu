@@ -196,6 +196,7 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blo
   extern __shared__ unsigned long long remv[];   // col_blocks words
   __shared__ unsigned long long s_kept;
   __shared__ int s_count;
+  __shared__ int s_rows[64];                     // kept rows of the current block
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < col_blocks; i += SWEEP_THREADS) remv[i] = 0;
   if (tid == 0) s_count = 0;
@@ -240,16 +241,39 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blo
     __syncthreads();
     const unsigned long long K = s_kept;
     if (s_count >= limit) break;
-    // OR the kept rows of this block into the removal bitmap for later column blocks
-    for (int j = b + 1 + tid; j < col_blocks; j += SWEEP_THREADS) {
-      unsigned long long acc = 0;
-      unsigned long long rem = K;
-      while (rem) {
-        const int i = __ffsll((long long)rem) - 1;
-        rem &= rem - 1;
-        acc |= mask[(size_t)(64 * b + i) * col_blocks + j];
+    // OR the kept rows of this block into the removal bitmap of the later column blocks.
+    // (kept row, column) pairs are spread over the whole CTA -- RP row parts x columns --
+    // and every thread issues its loads four at a time before using them: one thread per
+    // column walking its <= 64 rows serialised 64 L2 latencies per block (17 us/block).
+    const int nc = col_blocks - (b + 1);
+    if (nc > 0 && K != 0ull) {
+      if (tid < 64) {
+        if ((K >> tid) & 1ull) s_rows[__popcll(K & ((1ull << tid) - 1ull))] = tid;
       }
-      remv[j] |= acc;
+      __syncthreads();
+      const int kc = __popcll(K);
+      int rp_log2 = 0;
+      while (rp_log2 < 5 && ((nc << (rp_log2 + 1)) <= SWEEP_THREADS)) ++rp_log2;
+      const int RP = 1 << rp_log2;
+      const int part = tid & (RP - 1);
+      const int cols_per_pass = SWEEP_THREADS >> rp_log2;
+      const unsigned long long* mrow = mask + (size_t)(64 * b) * col_blocks + (b + 1);
+      for (int c = tid >> rp_log2; c < nc; c += cols_per_pass) {
+        unsigned long long acc = 0;
+        int ri = part;
+        for (; ri + 3 * RP < kc; ri += 4 * RP) {
+          const unsigned long long w0 = mrow[(size_t)s_rows[ri] * col_blocks + c];
+          const unsigned long long w1 = mrow[(size_t)s_rows[ri + RP] * col_blocks + c];
+          const unsigned long long w2 = mrow[(size_t)s_rows[ri + 2 * RP] * col_blocks + c];
+          const unsigned long long w3 = mrow[(size_t)s_rows[ri + 3 * RP] * col_blocks + c];
+          acc |= (w0 | w1) | (w2 | w3);
+        }
+        for (; ri < kc; ri += RP) acc |= mrow[(size_t)s_rows[ri] * col_blocks + c];
+        if (acc != 0ull) {
+          if (RP == 1) remv[b + 1 + c] |= acc;
+          else atomicOr(&remv[b + 1 + c], acc);
+        }
+      }
     }
     __syncthreads();
   }
