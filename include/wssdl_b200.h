@@ -216,6 +216,34 @@ int wssdl_anchor_labels(const float* gt_boxes, const int* num_gt, int max_gt,
                         double* max_overlap, void* workspace, size_t workspace_bytes,
                         wssdl_stream_t stream);
 
+/* ---------------------------------------------------------------- detection post-processing
+ * Replaces the tail of im_detect (fast_rcnn/test_bus.py:207-223: rois / im_scale,
+ * bbox_transform_inv per class, _clip_boxes :124-134) and the per-image body of test_net
+ * (fast_rcnn/test_bus.py:360-401; twin fast_rcnn/train_bus.py:453-514): per class j >= 1
+ * keep scores > score_thresh, greedy NMS (utils.cython_nms.nms: >= against a double
+ * threshold), optional class-agnostic NMS over the survivors (:371-386), cap at
+ * max_per_image over all classes (:394-401: keep scores >= the max_per_image-th largest).
+ * Batched: one CTA per image, nothing leaves the device.
+ *
+ * rois       [B*roi_stride,5] f32 (batch, x1,y1,x2,y2) in the SCALED frame; image b owns rows
+ *            [b*roi_stride, b*roi_stride + roi_counts[b]) (roi_counts NULL: all roi_stride)
+ *            -- the layout wssdl_proposals writes
+ * scores     [B*roi_stride,K] f32 class probabilities (column 0 = background)
+ * bbox_pred  [B*roi_stride,4K] f32 class-major deltas
+ * im_meta    [B,3] f32 rows (im_h, im_w of the UNSCALED image = im.shape[:2], im_scale)
+ * dets       [B,K,roi_stride,5] f32 (x1,y1,x2,y2,score), class j of image b in
+ *            descending-score order, det_counts [B,K] i32 valid rows (class 0: always 0);
+ *            unused rows are zero-filled
+ * pred_boxes [B*roi_stride,4K] f32 (may be NULL): the regressed + clipped boxes of :222-223
+ * status     int[1] (may be NULL): 1 if some visited pair had a zero union
+ * Limits: roi_stride <= 1024, K <= 64, (K-1)*roi_stride <= 1024 when cls_agnostic.
+ */
+int wssdl_detect_postprocess(const float* rois, const int* roi_counts, int roi_stride,
+                             const float* scores, const float* bbox_pred, const float* im_meta,
+                             int B, int K, float score_thresh, double nms_thresh,
+                             int max_per_image, int cls_agnostic, float* dets, int* det_counts,
+                             float* pred_boxes, int* status, wssdl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -351,3 +351,61 @@ def sample_rois(all_rois, gt_boxes, fg_rois_per_image, rois_per_image, num_class
         bbox_targets[ind, 4 * cls:4 * cls + 4] = data[ind, 1:]
         inside[ind, 4 * cls:4 * cls + 4] = cfg["BBOX_INSIDE_WEIGHTS"]
     return labels, rois, bbox_targets, inside, keep_inds
+
+
+# --------------------------------------------------------------- detection post-processing
+def im_detect_boxes(rois, bbox_pred, im_shape, im_scale, bbox_reg=True, num_classes=None):
+    """Tail of im_detect (fast_rcnn/test_bus.py:207-223): RoIs of ONE image back to the
+    original image frame, per-class box regression, clip.
+
+    rois [R,5] f32 (batch, x1,y1,x2,y2) in the scaled frame; bbox_pred [R,4K] f32;
+    im_shape = shape of the unscaled image (H, W[, ch]); im_scale python float.
+    Returns pred_boxes [R,4K] f32."""
+    boxes = rois[:, 1:5] / im_scale                                   # :209 (f32 / py float -> f32)
+    if bbox_reg:
+        pred_boxes = bbox_transform_inv(boxes, bbox_pred)             # :222
+        # _clip_boxes (:124-134): one-sided clips, unlike bbox_transform.clip_boxes
+        pred_boxes[:, 0::4] = np.maximum(pred_boxes[:, 0::4], 0)
+        pred_boxes[:, 1::4] = np.maximum(pred_boxes[:, 1::4], 0)
+        pred_boxes[:, 2::4] = np.minimum(pred_boxes[:, 2::4], im_shape[1] - 1)
+        pred_boxes[:, 3::4] = np.minimum(pred_boxes[:, 3::4], im_shape[0] - 1)
+    else:
+        pred_boxes = np.tile(boxes, (1, num_classes))                 # :226
+    return pred_boxes
+
+
+def detections_postprocess(scores, boxes, thresh=0.05, nms_thresh=None, max_per_image=300,
+                         cls_agnostic_nms=False):
+    """Per-image body of test_net (fast_rcnn/test_bus.py:360-401).
+
+    scores [R,K] f32, boxes [R,4K] f32 -> list over classes (entry 0 = background = empty)
+    of [n_j,5] f32 (x1,y1,x2,y2,score) in descending-score order."""
+    nms_thresh = TEST['NMS'] if nms_thresh is None else nms_thresh
+    K = scores.shape[1]
+    out = [np.zeros((0, 5), np.float32) for _ in range(K)]
+    for j in range(1, K):                                             # :360 skip background
+        inds = np.where(scores[:, j] > thresh)[0]                     # :361
+        cls_scores = scores[inds, j]
+        cls_boxes = boxes[inds, j * 4:(j + 1) * 4]
+        cls_dets = np.hstack((cls_boxes, cls_scores[:, np.newaxis])).astype(np.float32, copy=False)
+        keep = _nms(cls_dets, nms_thresh)                             # :366 utils.cython_nms.nms
+        out[j] = cls_dets[keep, :]
+    if cls_agnostic_nms:                                              # :371-386
+        all_dets = np.zeros((0, 6), dtype=np.float32)
+        for j in range(1, K):
+            all_dets = np.concatenate(
+                (all_dets, np.hstack((out[j], j * np.ones((out[j].shape[0], 1), dtype=np.float32)))),
+                axis=0)
+        keep = _nms(all_dets, nms_thresh)
+        all_dets = all_dets[keep, :]
+        for j in range(1, K):
+            inds = np.where(all_dets[:, 5] == j)[0]
+            out[j] = all_dets[inds, :5]
+    if max_per_image > 0:                                             # :394-401
+        image_scores = np.hstack([out[j][:, -1] for j in range(1, K)])
+        if len(image_scores) > max_per_image:
+            image_thresh = np.sort(image_scores)[-max_per_image]
+            for j in range(1, K):
+                keep = np.where(out[j][:, -1] >= image_thresh)[0]
+                out[j] = out[j][keep, :]
+    return out

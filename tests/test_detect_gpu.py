@@ -1,0 +1,93 @@
+"""Per-class detection post-processing (fast_rcnn/test_bus.py:207-223, :360-401) on the GPU
+against the numpy restatement composed from the pinned oracles (oracle.layers)."""
+import numpy as np
+import pytest
+import torch
+
+from wssdl_bus_b200 import ops, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # regressed boxes: exp() is 1 ulp away from numpy's
+
+
+def _inputs(seed, B, S, K, counts=None, im_hw=(437, 583), im_scale=600.0 / 437):
+    """RoIs like the proposal layer emits them (scaled frame), fixed stride S per image."""
+    rois = np.zeros((B * S, 5), np.float32)
+    for b in range(B):
+        r = syn.rois_for_pool(seed + b, S, 1, im_w=int(im_hw[1] * im_scale), im_h=int(im_hw[0] * im_scale))
+        r[:, 0] = b
+        rois[b * S:(b + 1) * S] = r
+    scores, deltas = syn.rcnn_head_outputs(seed, B * S, K)
+    meta = np.tile(np.array([[im_hw[0], im_hw[1], im_scale]], np.float32), (B, 1))
+    return rois, scores, deltas, meta
+
+
+def _oracle(oracle_mod, rois, scores, deltas, meta, S, counts, pred_boxes, **kw):
+    """Reference flow per image.  The discrete steps are fed the DEVICE-regressed boxes so
+    they can be compared bit-exactly (exp ulp differences would otherwise flip NMS ties)."""
+    B = meta.shape[0]
+    outs = []
+    for b in range(B):
+        n = S if counts is None else int(counts[b])
+        sl = slice(b * S, b * S + n)
+        outs.append(oracle_mod.layers.detections_postprocess(scores[sl], pred_boxes[sl], **kw))
+    return outs
+
+
+@pytest.mark.parametrize("B,S,K,agn,cap", [(1, 300, 3, False, 300), (4, 300, 3, False, 40),
+                                           (3, 300, 3, True, 300), (2, 128, 5, True, 25),
+                                           (2, 1000, 2, False, 100), (5, 64, 21, False, 0)])
+def test_postprocess_matches_reference_flow(oracle_mod, B, S, K, agn, cap):
+    rois, scores, deltas, meta = _inputs(700 + S + K, B, S, K)
+    counts = None
+    if B > 1:
+        counts = np.full((B,), S, np.int32)
+        counts[1] = S // 3
+        counts[-1] = 0 if B > 2 else S - 1
+    out = ops.detect_postprocess(rois, scores, deltas, meta, roi_counts=counts, roi_stride=S,
+                                 score_thresh=0.05, nms_thresh=0.3, max_per_image=cap,
+                                 cls_agnostic=agn, want_pred_boxes=True)
+    pred = out["pred_boxes"].cpu().numpy()
+    # 1. regressed + clipped boxes vs the reference arithmetic (tolerance: exp)
+    for b in range(B):
+        n = S if counts is None else int(counts[b])
+        sl = slice(b * S, b * S + n)
+        want = oracle_mod.layers.im_detect_boxes(rois[sl], deltas[sl], (meta[b, 0], meta[b, 1]),
+                                                 float(meta[b, 2]))
+        np.testing.assert_allclose(pred[sl], want, rtol=RTOL, atol=1e-3)
+    # 2. threshold / NMS / agnostic NMS / cap: bit-exact given the same boxes
+    want = _oracle(oracle_mod, rois, scores, deltas, meta, S, counts, pred, thresh=np.float32(0.05),
+                   nms_thresh=0.3, max_per_image=cap, cls_agnostic_nms=agn)
+    dets = out["dets"].cpu().numpy()
+    cnt = out["counts"].cpu().numpy()
+    assert int(out["status"].item()) == 0
+    for b in range(B):
+        assert cnt[b, 0] == 0
+        for j in range(1, K):
+            got = dets[b, j, :cnt[b, j]]
+            assert got.shape == want[b][j].shape, (b, j, got.shape, want[b][j].shape)
+            assert np.array_equal(got, want[b][j])
+            assert not dets[b, j, cnt[b, j]:].any()          # padding is zero-filled
+
+
+def test_reference_named_wrappers(oracle_mod):
+    from wssdl_bus_b200.fast_rcnn import test_bus
+    rois, scores, deltas, meta = _inputs(900, 2, 300, 3)
+    all_boxes, out = test_bus.test_net_batch(rois, scores, deltas, meta[:, :2], meta[:, 2], roi_stride=300)
+    assert len(all_boxes) == 3 and len(all_boxes[1]) == 2 and all_boxes[0][0].shape == (0, 5)
+    pb = test_bus.detect_boxes(rois[:300], deltas[:300], (437, 583, 3), float(meta[0, 2]))
+    want = oracle_mod.layers.detections_postprocess(scores[:300], pb, thresh=np.float32(0.05))
+    got = test_bus.postprocess_detections(scores[:300], pb)
+    for j in range(3):
+        assert np.array_equal(got[j], want[j]) and np.array_equal(all_boxes[j][0], want[j])
+
+
+def test_limits_and_empty():
+    from wssdl_bus_b200 import _lib
+    rois, scores, deltas, meta = _inputs(901, 1, 8, 3)
+    out = ops.detect_postprocess(rois, scores, deltas, meta, score_thresh=2.0)   # nothing passes
+    assert int(out["counts"].sum()) == 0 and not out["dets"].any()
+    with pytest.raises(_lib.WssdlError):
+        ops.detect_postprocess(np.zeros((2000, 5), np.float32), np.zeros((2000, 3), np.float32),
+                               np.zeros((2000, 12), np.float32), meta)

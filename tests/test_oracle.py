@@ -198,3 +198,29 @@ def test_proposal_layer_restatement_properties(oracle_mod):
         # clip is idempotent
         d = p["decoded"].copy()
         assert np.array_equal(L.clip_boxes(d.copy(), info[b, :2]), d)
+
+
+def test_detections_postprocess_restatement_properties(oracle_mod):
+    """Control flow of fast_rcnn/test_bus.py:360-401 (unpinned by the reference: no fixtures):
+    survivors are a subset of the thresholded boxes in descending-score order, the cap keeps
+    the top max_per_image scores, class-agnostic NMS never adds boxes."""
+    R, K = 300, 3
+    rois = syn.rois_for_pool(5, R)
+    scores, deltas = syn.rcnn_head_outputs(6, R, K)
+    assert len(np.unique(scores)) == scores.size
+    pb = oracle_mod.layers.im_detect_boxes(rois, deltas, (437, 583, 3), 600.0 / 437)
+    assert pb.shape == (R, 4 * K) and pb.dtype == np.float32
+    assert (pb[:, 0::4] >= 0).all() and (pb[:, 2::4] <= 582).all() and (pb[:, 3::4] <= 436).all()
+    base = oracle_mod.layers.detections_postprocess(scores, pb, max_per_image=0)
+    assert base[0].shape == (0, 5)
+    for j in range(1, K):
+        d = base[j]
+        assert (d[:, 4] > 0.05).all() and (np.diff(d[:, 4]) < 0).all()
+        assert set(map(tuple, d[:, :4])) <= set(map(tuple, pb[:, 4 * j:4 * j + 4]))
+    capped = oracle_mod.layers.detections_postprocess(scores, pb, max_per_image=20)
+    assert sum(len(c) for c in capped) == 20
+    top = np.sort(np.concatenate([b[:, 4] for b in base]))[-20:]
+    assert np.array_equal(np.sort(np.concatenate([c[:, 4] for c in capped])), top)
+    agn = oracle_mod.layers.detections_postprocess(scores, pb, max_per_image=0, cls_agnostic_nms=True)
+    for j in range(1, K):
+        assert set(map(tuple, agn[j])) <= set(map(tuple, base[j]))

@@ -13,6 +13,7 @@
 // reference's expression tree (bbox.c:2068: ((bw*bh)+qarea)-(iw*ih), then (iw*ih)/ua) is
 // evaluated with exactly one rounding per operation, which makes the fp64 path bit-exact.
 #include "common.cuh"
+#include "box_common.cuh"
 
 namespace {
 
@@ -141,9 +142,6 @@ int launch_overlaps(const T* boxes, int N, const T* query, int K, int kind, T* o
   return WSSDL_OK;
 }
 
-// exp in fp64, rounded once to fp32: correctly rounded expf (np.exp on fp32 is within 1 ulp)
-__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
-
 // bbox_transform_inv: one thread per (row, class) group of 4 deltas
 __global__ void bbox_transform_inv_kernel(const float* __restrict__ boxes,
                                           const float* __restrict__ deltas, long long N, int k,
@@ -152,20 +150,9 @@ __global__ void bbox_transform_inv_kernel(const float* __restrict__ boxes,
   if (idx >= N * k) return;
   const long long n = idx / k;
   const float x1 = boxes[4 * n], y1 = boxes[4 * n + 1], x2 = boxes[4 * n + 2], y2 = boxes[4 * n + 3];
-  const float w = __fadd_rn(__fsub_rn(x2, x1), 1.0f);                 // :36
-  const float h = __fadd_rn(__fsub_rn(y2, y1), 1.0f);
-  const float cx = __fadd_rn(x1, __fmul_rn(0.5f, w));                 // :38
-  const float cy = __fadd_rn(y1, __fmul_rn(0.5f, h));
-  const float dx = deltas[4 * idx], dy = deltas[4 * idx + 1];
-  const float dw = deltas[4 * idx + 2], dh = deltas[4 * idx + 3];
-  const float pcx = __fadd_rn(__fmul_rn(dx, w), cx);                  // :46
-  const float pcy = __fadd_rn(__fmul_rn(dy, h), cy);
-  const float pw = __fmul_rn(exp_cr(dw), w);                          // :48
-  const float ph = __fmul_rn(exp_cr(dh), h);
-  out[4 * idx] = __fsub_rn(pcx, __fmul_rn(0.5f, pw));                 // :53-59
-  out[4 * idx + 1] = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
-  out[4 * idx + 2] = __fadd_rn(pcx, __fmul_rn(0.5f, pw));
-  out[4 * idx + 3] = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+  const float4 o = decode_box(x1, y1, x2, y2, deltas[4 * idx], deltas[4 * idx + 1],
+                              deltas[4 * idx + 2], deltas[4 * idx + 3]);
+  out[4 * idx] = o.x; out[4 * idx + 1] = o.y; out[4 * idx + 2] = o.z; out[4 * idx + 3] = o.w;
 }
 
 __device__ __forceinline__ float clipf(float v, float hi) {

@@ -406,3 +406,46 @@ def anchor_labels(gt_boxes, num_gt, im_info, H, W, base_anchors, feat_stride, da
             _ptr(labels), _ptr(argmax), _ptr(maxov), _vp(ws.data_ptr()), ws.numel(), _stream(dev))
     _lib.check(rc, "wssdl_anchor_labels")
     return labels, argmax, maxov
+
+
+# ------------------------------------------------------------------ detection post-processing
+def detect_postprocess(rois, scores, bbox_pred, im_meta, roi_counts=None, roi_stride=None,
+                       score_thresh=0.05, nms_thresh=0.3, max_per_image=300, cls_agnostic=False,
+                       want_pred_boxes=False):
+    """Batched tail of im_detect + per-image body of test_net (fast_rcnn/test_bus.py:207-223,
+    :360-401).  rois [B*S,5] (scaled frame, image b = rows [b*S, b*S+roi_counts[b])), scores
+    [B*S,K], bbox_pred [B*S,4K], im_meta [B,3] = (im_h, im_w of the unscaled image, im_scale).
+    Returns dict of device tensors: dets [B,K,S,5] (x1,y1,x2,y2,score; class-j rows in
+    descending-score order), counts [B,K] i32, status i32 [1] (+ pred_boxes [B*S,4K])."""
+    scores = _cuda(scores, torch.float32)
+    dev = scores.device
+    rois = _cuda(rois, torch.float32, dev)
+    bbox_pred = _cuda(bbox_pred, torch.float32, dev)
+    im_meta = _cuda(im_meta, torch.float32, dev)
+    if im_meta.dim() == 1:
+        im_meta = im_meta.reshape(1, -1)
+    B = im_meta.shape[0]
+    if rois.dim() != 2 or rois.shape[1] != 5 or scores.dim() != 2:
+        raise ValueError("rois [B*S,5], scores [B*S,K]")
+    K = scores.shape[1]
+    S = int(roi_stride) if roi_stride is not None else (rois.shape[0] // max(B, 1))
+    if (rois.shape[0] != B * S or scores.shape[0] != B * S or im_meta.shape[1] != 3
+            or tuple(bbox_pred.shape) != (B * S, 4 * K)):
+        raise ValueError("shape mismatch: rois [B*S,5], scores [B*S,K], bbox_pred [B*S,4K], "
+                         "im_meta [B,3]")
+    counts_in = _cuda(roi_counts, torch.int32, dev) if roi_counts is not None else None
+    with torch.cuda.device(dev):
+        dets = torch.empty((B, K, S, 5), dtype=torch.float32, device=dev)
+        counts = torch.empty((B, K), dtype=torch.int32, device=dev)
+        status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        pred = (torch.empty((B * S, 4 * K), dtype=torch.float32, device=dev)
+                if want_pred_boxes else None)
+        rc = _lib.lib().wssdl_detect_postprocess(
+            _ptr(rois), _ptr(counts_in), S, _ptr(scores), _ptr(bbox_pred), _ptr(im_meta), B, K,
+            float(score_thresh), float(nms_thresh), int(max_per_image), int(bool(cls_agnostic)),
+            _ptr(dets), _vp(counts.data_ptr()), _ptr(pred), _vp(status.data_ptr()), _stream(dev))
+    _lib.check(rc, "wssdl_detect_postprocess")
+    out = dict(dets=dets, counts=counts, status=status)
+    if want_pred_boxes:
+        out["pred_boxes"] = pred
+    return out

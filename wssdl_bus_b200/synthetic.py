@@ -122,3 +122,24 @@ def gt_boxes(seed, B, max_gt=20, im_w=800, im_h=600, n_fg=(1, 3), n_bg=(0, 2)):
         gt[b, :nf, 4] = rng.integers(1, 3, nf)
         num[b] = nf + nb
     return gt, num
+
+
+def rcnn_head_outputs(seed, n_rows, K=3, delta_std=0.1):
+    """Synthetic RCNN head outputs for n_rows RoIs: cls_prob [n_rows,K] f32 (rows sum to ~1,
+    every entry a distinct fp32 value so NMS order is well defined) and bbox_pred [n_rows,4K]
+    f32 ~ N(0, delta_std) with dw, dh clipped to +-1."""
+    rng = np.random.default_rng(seed + 32452843)
+    n = n_rows * K
+    u = ((rng.permutation(n) + 0.5) / n).astype(np.float64).reshape(n_rows, K)
+    u[:, 0] *= 3.0                                      # background usually wins
+    p = (u / u.sum(1, keepdims=True)).astype(np.float32)
+    # normalisation can merge neighbours: nudge duplicates apart (deterministically)
+    flat = p.reshape(-1)
+    order = np.argsort(flat, kind="stable")
+    for a, b in zip(order[:-1], order[1:]):
+        if flat[b] <= flat[a]:
+            flat[b] = np.nextafter(flat[a], np.float32(2.0))
+    d = (rng.standard_normal((n_rows, 4 * K)) * delta_std).astype(np.float32)
+    d4 = d.reshape(n_rows, K, 4)
+    np.clip(d4[..., 2:], -1.0, 1.0, out=d4[..., 2:])
+    return p, d
