@@ -185,6 +185,21 @@ def main():
                     t0 = time.perf_counter()
                     fn(bn, qn)
                     emit(out, op="cpu_bbox_overlaps", N=n, K=k, ms=(time.perf_counter() - t0) * 1e3)
+    if want("detect"):
+        for B in (1, 256):
+            S, K = 300, 3
+            rois = np.concatenate([syn.rois_for_pool(9 + b, S) for b in range(B)])
+            scores, deltas = syn.rcnn_head_outputs(9, B * S, K)
+            meta = np.tile(np.array([[437, 583, 600.0 / 437]], np.float32), (B, 1))
+            a = [torch.from_numpy(v).cuda() for v in (rois, scores, deltas, meta)]
+            med, best = timeit(lambda: ops.detect_postprocess(*a, roi_stride=S), iters=10, flush=False)
+            emit(out, op="detect_postprocess", B=B, S=S, K=K, ms=med, ms_min=best, images_per_s=B / med * 1e3)
+            if args.cpu and B == 1:
+                import oracle
+                t0 = time.perf_counter()
+                pb = oracle.layers.im_detect_boxes(rois, deltas, (437, 583), 600.0 / 437)
+                oracle.layers.detections_postprocess(scores, pb, thresh=np.float32(0.05))
+                emit(out, op="cpu_detect_postprocess", B=1, ms=(time.perf_counter() - t0) * 1e3)
     if want("labels"):
         from wssdl_bus_b200.rpn_msr.generate_anchors import generate_anchors
         for B in (1, 64):

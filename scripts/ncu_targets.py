@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Small driver for ncu captures of the secondary kernels (one shape each, few launches):
+   python scripts/ncu_targets.py nms|iou|detect|bwd"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from wssdl_bus_b200 import ops, synthetic as syn  # noqa: E402
+
+what = sys.argv[1]
+if what == "nms":
+    d = torch.from_numpy(syn.dets(7, 20000)).cuda()
+    for _ in range(3):
+        ops.nms_device(d, 0.7)
+elif what == "iou":
+    b = torch.from_numpy(syn.random_boxes(3, 20000).astype(np.float64)).cuda()
+    for dt in (torch.float64, torch.float32):
+        for _ in range(3):
+            ops.bbox_overlaps_device(b.to(dt), b.to(dt), ops.IOU, dt)
+elif what == "detect":
+    B, S, K = 256, 300, 3
+    rois = np.concatenate([syn.rois_for_pool(9 + b, S) for b in range(B)])
+    scores, deltas = syn.rcnn_head_outputs(9, B * S, K)
+    meta = np.tile(np.array([[437, 583, 600.0 / 437]], np.float32), (B, 1))
+    args = [torch.from_numpy(v).cuda() for v in (rois, scores, deltas, meta)]
+    for _ in range(3):
+        ops.detect_postprocess(*args, roi_stride=S)
+elif what == "bwd":
+    B, H, W, C = 16, 38, 50, 1024
+    x = torch.from_numpy(syn.feature_map(1, B, H, W, C)).cuda()
+    r = torch.from_numpy(syn.rois_for_pool(5, B * 300, B)).cuda()
+    top, arg = ops.roi_pool_forward(x, r, 14, 14, 1 / 16.)
+    g = torch.randn_like(top)
+    for _ in range(3):
+        ops.roi_pool_backward((B, H, W, C), r, arg, g, 14, 14, 1 / 16.)
+torch.cuda.synchronize()

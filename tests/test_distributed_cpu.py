@@ -21,7 +21,8 @@ def _worker(rank, world, port, n_images, post, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from wssdl_bus_b200.pipeline import all_gather_detections, shard_images, unshard_detections
+    from wssdl_bus_b200.pipeline import (all_gather_blobs, all_gather_detections, shard_images,
+                                         unshard_detections)
     mine = shard_images(n_images, rank, world)
     n_local = (n_images + world - 1) // world
     det = torch.zeros((n_local, post, 5))
@@ -34,6 +35,11 @@ def _worker(rank, world, port, n_images, post, ret):
     d, c = unshard_detections(det_all, cnt_all, n_images)
     ok = d.shape == (n_images, post, 5) and all(float(d[i, 0, 0]) == i for i in range(n_images))
     ok = ok and c.tolist() == [i % post + 1 for i in range(n_images)]
+    # the bench's form: boxes, scores and counts gathered as separate blobs (no concat kernel)
+    boxes, scores, counts = all_gather_blobs([det, det[:, :, 4].contiguous(), cnt])
+    d2, c2 = unshard_detections(boxes, counts, n_images)
+    s2, _ = unshard_detections(scores, counts, n_images)
+    ok = ok and torch.equal(d2, d) and torch.equal(c2, c) and torch.equal(s2, d[:, :, 4])
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -27,9 +27,10 @@ def test_hot_path_matches_oracle_chain(oracle_mod):
     assert np.array_equal(p["top"].cpu().numpy(), wt)
     assert np.array_equal(p["argmax"].cpu().numpy(), wa)
     assert p["counts"].cpu().numpy().tolist() == [300] * B
-    det, cnt = hot.detections(p)
-    assert det.shape == (B, 300, 5) and cnt.shape == (B,)
-    assert bool(torch.all(det[:, :-1, 4] > det[:, 1:, 4]))          # descending scores
+    boxes, scores, cnt = hot.detections(p)
+    assert boxes.shape == (B, 300, 5) and scores.shape == (B, 300) and cnt.shape == (B,)
+    assert boxes.data_ptr() == p["rois"].data_ptr()                   # views, no copy kernel
+    assert bool(torch.all(scores[:, :-1] > scores[:, 1:]))            # descending scores
 
 
 def test_host_pipeline_equals_device_path():

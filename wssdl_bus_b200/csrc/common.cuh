@@ -27,6 +27,16 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// inter / den for an IoU whose numerator is very often exactly zero (boxes that do not
+// touch).  __fdiv_rn sends a zero numerator down its slow path (FCHK fails -> CALL), which
+// made the NMS mask kernel spend half of its instructions there (ncu: 85 instructions per
+// pair).  The shortcut returns what IEEE division would, up to the sign of zero, which no
+// caller observes (the quotient is only compared against a threshold): 0/0 and 0/NaN = NaN.
+__device__ __forceinline__ float iou_quotient(float inter, float den) {
+  if (inter == 0.0f) return (den == 0.0f || den != den) ? __int_as_float(0x7fc00000) : 0.0f;
+  return __fdiv_rn(inter, den);
+}
+
 // RoI geometry in feature-map cells, computed exactly as the reference does
 // (roi_pooling_op.cc:153-165): C round() = half away from zero, float products.
 struct RoiCells {

@@ -164,12 +164,22 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blo
   __syncthreads();
   const int limit = max_keep > 0 ? min(max_keep, N) : N;
 
+  // diagonal words of rows 64b+lane and 64b+32+lane (warp 0), fetched one block ahead: they
+  // do not depend on the removal bitmap, only their interpretation does
+  unsigned long long nd0 = 0ull, nd1 = 0ull;
+  if (tid < 32) {
+    nd0 = lane < N ? mask[(size_t)lane * col_blocks] : 0ull;
+    nd1 = lane + 32 < N ? mask[(size_t)(lane + 32) * col_blocks] : 0ull;
+  }
   for (int b = 0; b < col_blocks; ++b) {
     if (tid < 32) {
-      // diagonal words of rows 64b+lane and 64b+32+lane
       const int r0 = 64 * b + lane, r1 = r0 + 32;
-      const unsigned long long d0 = r0 < N ? mask[(size_t)r0 * col_blocks + b] : 0ull;
-      const unsigned long long d1 = r1 < N ? mask[(size_t)r1 * col_blocks + b] : 0ull;
+      const unsigned long long d0 = nd0, d1 = nd1;
+      if (b + 1 < col_blocks) {
+        const int q0 = r0 + 64, q1 = r1 + 64;
+        nd0 = q0 < N ? mask[(size_t)q0 * col_blocks + b + 1] : 0ull;
+        nd1 = q1 < N ? mask[(size_t)q1 * col_blocks + b + 1] : 0ull;
+      }
       const int nrow = min(64, N - 64 * b);
       const unsigned long long valid = nrow == 64 ? ~0ull : ((1ull << nrow) - 1ull);
       const unsigned long long alive = ~remv[b] & valid;
@@ -222,6 +232,12 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blo
       for (int c = tid >> rp_log2; c < nc; c += cols_per_pass) {
         unsigned long long acc = 0;
         int ri = part;
+        for (; ri + 7 * RP < kc; ri += 8 * RP) {
+          unsigned long long w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = mrow[(size_t)s_rows[ri + u * RP] * col_blocks + c];
+          acc |= ((w[0] | w[1]) | (w[2] | w[3])) | ((w[4] | w[5]) | (w[6] | w[7]));
+        }
         for (; ri + 3 * RP < kc; ri += 4 * RP) {
           const unsigned long long w0 = mrow[(size_t)s_rows[ri] * col_blocks + c];
           const unsigned long long w1 = mrow[(size_t)s_rows[ri + RP] * col_blocks + c];

@@ -34,14 +34,14 @@ __device__ __forceinline__ bool suppresses(const float4 bi, float ai, const floa
   const float inter = __fmul_rn(w, h);
   const float den = __fsub_rn(__fadd_rn(ai, aj), inter);
   if (den == 0.0f) *zero = true;
-  const float ovr = __fdiv_rn(inter, den);
+  const float ovr = iou_quotient(inter, den);
   bool s = th.use_gt ? (ovr > th.gt) : (ovr >= th.ge);
   if (th.contain) {
     // nms.pyx:117-120: float division, compared against the double 0.95: x > 0.95 for a float x
     // is x > 0.949999988f (the largest float below 0.95), i.e. x >= 0.95000005f
     const float c95 = 0.949999988079071044921875f;
     if (ai == 0.0f || aj == 0.0f) *zero = true;   // the reference raises there as well
-    s = s || (__fdiv_rn(inter, ai) > c95) || (__fdiv_rn(inter, aj) > c95);
+    s = s || (iou_quotient(inter, ai) > c95) || (iou_quotient(inter, aj) > c95);
   }
   return s;
 }

@@ -114,7 +114,7 @@ __device__ __forceinline__ bool iou_ge(const float4 bi, float ai, const float4 b
   const float h = rmax(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
   const float inter = __fmul_rn(w, h);
   const float den = __fsub_rn(__fadd_rn(ai, aj), inter);
-  return __fdiv_rn(inter, den) >= thr_ge;
+  return iou_quotient(inter, den) >= thr_ge;
 }
 
 // K-th largest (1-based) among n keys in shared memory, considering only keys accepted by

@@ -48,11 +48,27 @@ class HotPath:
         return p
 
     def detections(self, p):
-        """Fixed-stride per-image detections [B, post, 5] (x1,y1,x2,y2,score) + counts [B]:
-        the tensors that are all-gathered."""
+        """Fixed-stride per-image detections: boxes [B, post, 5] (batch, x1,y1,x2,y2), scores
+        [B, post], counts [B] -- views of the kernel outputs (no copy, no extra launch); these
+        are the tensors that are all-gathered."""
         B = p["counts"].shape[0]
-        det = torch.cat([p["rois"][:, 1:5], p["scores"][:, None]], dim=1)
-        return det.reshape(B, self.post, 5), p["counts"]
+        return p["rois"].view(B, self.post, 5), p["scores"].view(B, self.post), p["counts"]
+
+
+def all_gather_blobs(tensors, group=None):
+    """all_gather_into_tensor of several [n_local, ...] tensors (NCCL over NVLink on GPUs,
+    gloo in the CPU tests): -> list of [world, n_local, ...]."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = []
+    for t in tensors:
+        if world == 1:
+            out.append(t[None])
+            continue
+        g = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(g, t.contiguous(), group=group)
+        out.append(g.reshape((world, t.shape[0]) + tuple(t.shape[1:])))
+    return out
 
 
 def all_gather_detections(det, counts, group=None):
@@ -90,20 +106,27 @@ class HostPipeline:
     copied back to pinned host memory.  Two CUDA streams double-buffer the chunks so the
     H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i."""
 
-    def __init__(self, hot, B, H, W, C, A, info_cols=3, chunk=32, device=None, need_argmax=True):
+    def __init__(self, hot, B, H, W, C, A, info_cols=3, chunk=32, device=None, need_argmax=True,
+                 features_to_host=True):
+        """features_to_host=False keeps the pooled features (and argmax) on the device -- the
+        reference's own arrangement, where fc6 consumes them on the GPU and only the RoIs
+        cross the py_func boundary (network.py:216); the kernels still run in full."""
         self.hot, self.B, self.chunk = hot, B, min(chunk, B)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.need_argmax = need_argmax
+        self.features_to_host = features_to_host
         post, ph, pw = hot.post, hot.pooled_h, hot.pooled_w
         pin = dict(pin_memory=True)
         self.h_out = dict(
             rois=torch.empty((B * post, 5), dtype=torch.float32, **pin),
             scores=torch.empty((B * post,), dtype=torch.float32, **pin),
             counts=torch.empty((B,), dtype=torch.int32, **pin),
-            top=torch.empty((B * post, ph, pw, C), dtype=torch.float32, **pin),
         )
-        if need_argmax:
-            self.h_out["argmax"] = torch.empty((B * post, ph, pw, C), dtype=torch.int32, **pin)
+        if features_to_host:
+            self.h_out["top"] = torch.empty((B * post, ph, pw, C), dtype=torch.float32, **pin)
+            if need_argmax:
+                self.h_out["argmax"] = torch.empty((B * post, ph, pw, C), dtype=torch.int32, **pin)
+        self.d_last = None      # device outputs of the last chunk (features_to_host=False)
         self.streams = [torch.cuda.Stream(self.device) for _ in range(2)]
         n = self.chunk
         dev = self.device
@@ -138,9 +161,12 @@ class HostPipeline:
                 self.h_out["rois"][b0 * post:b1 * post].copy_(rois, non_blocking=True)
                 self.h_out["scores"][b0 * post:b1 * post].copy_(p["scores"], non_blocking=True)
                 self.h_out["counts"][b0:b1].copy_(p["counts"], non_blocking=True)
-                self.h_out["top"][b0 * post:b1 * post].copy_(p["top"], non_blocking=True)
-                if self.need_argmax:
-                    self.h_out["argmax"][b0 * post:b1 * post].copy_(p["argmax"], non_blocking=True)
+                if self.features_to_host:
+                    self.h_out["top"][b0 * post:b1 * post].copy_(p["top"], non_blocking=True)
+                    if self.need_argmax:
+                        self.h_out["argmax"][b0 * post:b1 * post].copy_(p["argmax"], non_blocking=True)
+                else:
+                    self.d_last = p
         for s in self.streams:
             cur.wait_stream(s)
         cur.synchronize()
