@@ -171,6 +171,11 @@ roi_pool_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
 //   - bin edges of a batch of RoIs are computed once per CTA with the reference's float
 //     expressions (roi_cells / bin_lo / bin_hi) and kept packed in shared memory;
 //   - warps draw 32 items at a time from a shared counter (RoI sizes vary widely);
+//   - tried and dropped: routing the outputs through shared-memory staging and
+//     cp.async.bulk shared->global copies (64 B per bin column and tensor) to take the stores
+//     off the LSU data pipe -- bit-exact but 6.3 ms instead of 3.6 ms on the C4 workload: 64 B
+//     transfers are TMA-issue bound (about one per 3.7 cycles per SM) and the warps spin in
+//     wait_group.read (profiles/r01_roi_fwd_direct_vs_tiled.txt);
 //   - RoIs are grouped by image either by an in-CTA scan of the batch column (R <=
 //     T_SCAN_MAX_R, no workspace) or by a counting-sort pre-pass (roi_bucket_kernel) into
 //     the caller's workspace.  Bucket B collects RoIs whose batch index is outside [0,B):
@@ -742,7 +747,7 @@ TiledPlan plan_tiled(int B, int H, int W, int C, int R, int PH, int PW, bool vec
   if (!p.scan && workspace_bytes < tiled_workspace_bytes(B, R)) return p;
   if (!p.scan && (size_t)(B + 1) * sizeof(int) > (size_t)T_DYN_SMEM_MAX) return p;   // bucket counters
   const size_t map_bytes = (size_t)H * W * T_SLICE * sizeof(float);
-  const size_t list_bytes = p.scan ? sizeof(int) * (size_t)T_SCAN_MAX_R : 0;
+  const size_t list_bytes = p.scan ? sizeof(int) * (size_t)R : 0;
   const size_t budget = T_DYN_SMEM_MAX;
   if (map_bytes + list_bytes >= budget) return p;
   // per resident RoI: PH + PW packed edges, its index, cost class and sorted position
