@@ -134,6 +134,35 @@ def main():
         ru = torch.from_numpy(syn.rois_for_pool(5, 16 * 300, 16)).cuda()
         ru = ru[torch.argsort(ru[:, 0], stable=True)].contiguous()
         bench_roi(out, "C3 ResNet C4 16x1024, 4800 random RoIs 14x14", 16, 1024, 14, 14, ru)
+    if want("cpu") and args.cpu:
+        import oracle
+        c = syn.C1
+        feat = syn.feature_map(1, 1, 38, 50, 512)
+        cls, reg, info = syn.rpn_outputs(7, 1, 38, 50, 9)
+
+        def best_of(fn, n=3):
+            ts = []
+            for _ in range(n):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            return min(ts) * 1e3
+
+        blob = oracle.layers.proposal_layer(cls, reg, info)
+        for th in (1, oracle.clib.default_threads()):
+            emit(out, op="cpu_roi_pool_fwd", tag="C1 1x300", threads=th,
+                 ms=best_of(lambda: oracle.clib.roi_pool_fwd(feat, blob, 7, 7, 1 / 16., threads=th)))
+        top, arg = oracle.clib.roi_pool_fwd(feat, blob[:128], 7, 7, 1 / 16.)
+        g = np.ones_like(top)
+        emit(out, op="cpu_roi_pool_bwd", tag="C2 1x128", threads=oracle.clib.default_threads(),
+             ms=best_of(lambda: oracle.clib.roi_pool_bwd(g, arg, blob[:128], feat.shape, 1 / 16.)))
+        emit(out, op="cpu_proposal_layer", tag="TEST 6000->300", ms=best_of(
+            lambda: oracle.layers.proposal_layer(cls, reg, info), n=2))
+        emit(out, op="cpu_proposal_layer", tag="TRAIN 12000->2000", ms=best_of(
+            lambda: oracle.layers.proposal_layer(cls, reg, info, is_training=True), n=1))
+        gt, num = syn.gt_boxes(9, 1)
+        emit(out, op="cpu_anchor_labels", B=1, ms=best_of(
+            lambda: oracle.layers.anchor_labels(38, 50, gt[0, :num[0]], info[0])))
     if want("proposals"):
         for B in (1, 16, 256):
             cls, reg, info = syn.rpn_outputs(7, B, 38, 50, 9)
