@@ -155,7 +155,7 @@ roi_pool_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
 // Forward, shared-memory resident channel slice ("tiled").
 //
 // The direct kernel above re-reads every RoI's cells from L2: with 300 overlapping RoIs on
-// a 38x50 map that is ~35x the map per image (ncu, profiles/r01_roi_pool_fwd_v2: 34 GB of
+// a 38x50 map that is ~35x the map per image (ncu, profiles/history/r01_roi_pool_fwd_v2: 34 GB of
 // L2->SM reads for 15.4 GB of output, the kernel stalls on long_scoreboard at 57 % of the
 // DRAM peak).  Here one CTA owns (image, 16-channel slice): the slice of the whole map
 // (H*W*64 B = 121.6 KB for 38x50) is staged ONCE into shared memory with cp.async, then
