@@ -183,13 +183,16 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from wssdl_bus_b200 import ops
-    from wssdl_bus_b200.pipeline import HostPipeline, HotPath, all_gather_blobs
+    from wssdl_bus_b200.pipeline import (HostPipeline, HotPath, all_gather_blobs,
+                                         bind_to_gpu_numa_node)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.images_per_gpu
@@ -317,6 +320,7 @@ def run_ours(args):
             "gpu_launches": (3 if tiled else 2) * K,
             "clocks": clocks,
             "rois_per_image": [int(counts.min()), int(counts.max())],
+            "numa_node_rank0": numa,
         }
         if e2e:
             ems = e2e_ms / K
@@ -341,7 +345,8 @@ def run_ours(args):
             if args.cpu_sample:
                 cmd += ["--cpu-sample", str(args.cpu_sample)]
             env = dict(os.environ, RANK="0", WORLD_SIZE="1", CUDA_VISIBLE_DEVICES="")
-            r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+            r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900,
+                               preexec_fn=lambda: os.sched_setaffinity(0, all_cpus))  # all host cores
             try:
                 line["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
             except Exception:

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Every kernel once on small shapes, for compute-sanitizer (memcheck / racecheck / synccheck):
+   compute-sanitizer --tool racecheck python scripts/sanitize_targets.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from wssdl_bus_b200 import ops, synthetic as syn  # noqa: E402
+from wssdl_bus_b200.rpn_msr.generate_anchors import generate_anchors  # noqa: E402
+
+B, H, W, C = 2, 38, 50, 32
+feat = torch.from_numpy(syn.feature_map(0, B, H, W, C)).cuda()
+rois = np.concatenate([syn.rois_for_pool(1, 90, B), syn.adversarial_rois(B, W, H)])
+for kern in ("direct", "tiled"):
+    os.environ["WSSDL_ROI_FWD_KERNEL"] = kern
+    for mode in ("cpu", "gpu"):
+        top, arg = ops.roi_pool_forward(feat, rois, 7, 7, 1 / 16., bin_mode=mode)
+# counting-sort pre-pass (R > 4096)
+big = syn.rois_for_pool(2, 4200, B)
+top2, arg2 = ops.roi_pool_forward(feat, big, 7, 7, 1 / 16.)
+os.environ.pop("WSSDL_ROI_FWD_KERNEL")
+g = torch.randn_like(top)
+for det in (False, True):
+    ops.roi_pool_backward((B, H, W, C), rois, arg, g, 7, 7, 1 / 16., deterministic=det)
+cls, reg, info = syn.rpn_outputs(3, B, H, W, 9)
+ops.proposals(cls, reg, info, generate_anchors(), 16, 6000, 300, 0.7, 16)
+ops.proposals(cls, reg, info, generate_anchors(), 16, 2000, 500, 0.7, 16, want_decoded=True)
+d = syn.dets(4, 5000)
+ops.nms(d, 0.7)
+ops.nms(d, 0.3, mode=ops.NMS_GT_F32 | ops.NMS_CONTAIN)
+b = syn.random_boxes(5, 3000).astype(np.float64)
+q = syn.random_boxes(6, 130).astype(np.float64)
+ops.bbox_overlaps(b, q)
+ops.bbox_overlaps_ui(b, q[:21])
+ops.bbox_overlaps_device(b.astype(np.float32), q.astype(np.float32), ops.IOU, torch.float32)
+gt, num = syn.gt_boxes(7, B)
+ops.anchor_labels(gt, num, info, H, W, generate_anchors(), 16)
+S, K = 300, 3
+r2 = np.concatenate([syn.rois_for_pool(8 + i, S) for i in range(B)])
+sc, dl = syn.rcnn_head_outputs(8, B * S, K)
+meta = np.tile(np.array([[437, 583, 600.0 / 437]], np.float32), (B, 1))
+ops.detect_postprocess(r2, sc, dl, meta, roi_stride=S)
+ops.detect_postprocess(r2, sc, dl, meta, roi_stride=S, cls_agnostic=True, max_per_image=40)
+ops.bbox_transform_inv(b[:, :4].astype(np.float32), np.zeros((3000, 12), np.float32))
+torch.cuda.synchronize()
+print("sanitize targets done")

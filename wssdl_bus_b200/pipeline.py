@@ -14,6 +14,32 @@ from .fast_rcnn.config import cfg
 from .rpn_msr.generate_anchors import generate_anchors
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Restrict this process to the CPUs of the NUMA node its GPU hangs off, BEFORE it pins
+    host memory: pinned pages are placed on the node of the allocating thread, and with one
+    process per GPU an unbound launcher puts every rank's staging buffers on one socket (the
+    8-GPU e2e leg then crosses the inter-socket link for most of its 16 GB per step).
+    Returns the node, or None when the topology is not visible (containers may hide sysfs)."""
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_images(n_images, rank, world_size):
     """Image i belongs to rank i mod world_size (round robin)."""
     return np.arange(rank, n_images, world_size, dtype=np.int64)
