@@ -44,3 +44,13 @@ def test_image_sharding_is_a_partition():
         allidx = np.concatenate(parts) if parts else np.zeros(0, int)
         assert sorted(allidx.tolist()) == list(range(n))
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_numa_binding_is_a_noop_without_a_visible_topology():
+    """bind_to_gpu_numa_node must never raise or shrink the affinity when the GPU / sysfs
+    topology is not visible (CPU-only containers, VMs with numa_node = -1)."""
+    import os
+    from wssdl_bus_b200.pipeline import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), int)
+    assert os.sched_getaffinity(0) <= before and len(os.sched_getaffinity(0)) > 0

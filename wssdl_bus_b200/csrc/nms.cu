@@ -207,6 +207,7 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blo
         keep[count + __popcll(K & ((1ull << lane) - 1ull))] = order[r0];
       if ((K >> (lane + 32)) & 1ull)
         keep[count + __popcll(K & ((1ull << (lane + 32)) - 1ull))] = order[r1];
+      __syncwarp();                       // every lane has read s_count (racecheck: WAR)
       if (lane == 0) { s_kept = K; s_count = count + take; }
     }
     __syncthreads();
