@@ -244,6 +244,30 @@ int wssdl_detect_postprocess(const float* rois, const int* roi_counts, int roi_s
                              int max_per_image, int cls_agnostic, float* dets, int* det_counts,
                              float* pred_boxes, int* status, wssdl_stream_t stream);
 
+/* ---------------------------------------------------------------- evaluation: detection matching
+ * Replaces the per-detection loop and the CorLoc pass of voc_eval_bus
+ * (datasets/voc_eval_bus.py:206-247, :161-204) on the detection blob of
+ * wssdl_detect_postprocess (after the all-gather): every detection of class j >= 1 is scored
+ * against its image's ground-truth boxes of that class in fp64 (reference operation order,
+ * bit-exact overlaps), best overlap = first maximum, then TP / FP / difficult / duplicate rules
+ * in descending-score order per image, which is the order the reference's global walk visits
+ * each image's detections in.  The argsort/cumsum/AP bookkeeping stays on the host.
+ *
+ * dets [B,K,S,5], det_counts [B,K]: as written by wssdl_detect_postprocess
+ * gt_boxes [B,G,5] f32 (x1,y1,x2,y2,cls) in the detections' frame, num_gt [B] i32,
+ * difficult [B,G] u8 (may be NULL = none difficult); G <= 64
+ * tp, fp, fp_froc [B,K,S] u8: flags per detection (rows >= count and class 0 are not touched /
+ *            zeroed; allocate zero-filled); fp_froc = score >= score_thresh and overlap <= ovthresh
+ * img_stats [B,K,2] i32: [0] image has GT of the class (counts toward ni), [1] some detection
+ *            with score >= score_thresh overlaps a GT by more than ovthresh (counts toward nok)
+ * npos [K] i32: non-difficult GT boxes per class (:135)
+ */
+int wssdl_eval_match(const float* dets, const int* det_counts, int B, int K, int S,
+                     const float* gt_boxes, const int* num_gt, const unsigned char* difficult,
+                     int G, double ovthresh, float score_thresh, unsigned char* tp,
+                     unsigned char* fp, unsigned char* fp_froc, int* img_stats, int* npos,
+                     wssdl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -409,3 +409,115 @@ def detections_postprocess(scores, boxes, thresh=0.05, nms_thresh=None, max_per_
                 keep = np.where(out[j][:, -1] >= image_thresh)[0]
                 out[j] = out[j][keep, :]
     return out
+
+
+# --------------------------------------------------------------- VOC / CorLoc / FROC evaluation
+def voc_ap(rec, prec, use_07_metric=False):
+    """datasets/voc_eval_bus.py:37-66."""
+    if use_07_metric:
+        ap = 0.
+        for t in np.arange(0., 1.1, 0.1):
+            if np.sum(rec >= t) == 0:
+                p = 0
+            else:
+                p = np.max(prec[rec >= t])
+            ap = ap + p / 11.
+    else:
+        mrec = np.concatenate(([0.], rec, [1.]))
+        mpre = np.concatenate(([0.], prec, [0.]))
+        for i in range(mpre.size - 1, 0, -1):
+            mpre[i - 1] = np.maximum(mpre[i - 1], mpre[i])
+        i = np.where(mrec[1:] != mrec[:-1])[0]
+        ap = np.sum((mrec[i + 1] - mrec[i]) * mpre[i + 1])
+    return ap
+
+
+def voc_eval_arrays(image_ids, confidence, BB, gt_bbox, gt_difficult, ovthresh=0.5,
+                    use_07_metric=False, score_thresh=0.5):
+    """voc_eval_bus (datasets/voc_eval_bus.py:68-281) for ONE class, from the point where the
+    reference has parsed its text/XML files (:129-160): image_ids [nd] ints (index into the
+    image list, in file order), confidence [nd], BB [nd,4]; gt_bbox[i] [G_i,4] and
+    gt_difficult[i] [G_i] bool for every image i (objects of this class only).
+    Returns (rec, prec, ap, ni, nok, num_all_fps, num_fp_per_img) like :281 (arr_ok omitted)."""
+    n_images = len(gt_bbox)
+    class_recs = [dict(bbox=np.asarray(gt_bbox[i], dtype=float).reshape(-1, 4),
+                       difficult=np.asarray(gt_difficult[i], dtype=bool).reshape(-1),
+                       det=[False] * len(gt_bbox[i])) for i in range(n_images)]
+    npos = sum(int(np.sum(~r['difficult'])) for r in class_recs)                  # :135
+    image_ids = np.asarray(image_ids, dtype=np.int64)
+    confidence = np.asarray(confidence, dtype=float)
+    BB = np.asarray(BB, dtype=float).reshape(-1, 4)
+    if len(image_ids) == 0:                                                          # :276-279
+        return -1, -1, -1, 0, 0, 0, [0] * n_images
+    sorted_ind = np.argsort(-confidence)                                             # :155
+    sorted_scores = np.sort(-confidence)
+    BB = BB[sorted_ind, :]
+    image_ids = image_ids[sorted_ind]
+    # CorLoc :161-204
+    ni = nok = 0
+    for i in range(n_images):
+        BBGT = class_recs[i]['bbox']
+        if BBGT.shape[0] > 0:
+            ni += 1
+            inds = np.where((image_ids == i) & (sorted_scores <= -score_thresh))[0]
+            if len(inds) == 0:
+                continue
+            bb = BB[inds, :]
+            bok = False
+            for j in range(BBGT.shape[0]):
+                ixmin = np.maximum(bb[:, 0], BBGT[j, 0])
+                iymin = np.maximum(bb[:, 1], BBGT[j, 1])
+                ixmax = np.minimum(bb[:, 2], BBGT[j, 2])
+                iymax = np.minimum(bb[:, 3], BBGT[j, 3])
+                iw = np.maximum(ixmax - ixmin + 1., 0.)
+                ih = np.maximum(iymax - iymin + 1., 0.)
+                inters = iw * ih
+                uni = ((BBGT[j, 2] - BBGT[j, 0] + 1.) * (BBGT[j, 3] - BBGT[j, 1] + 1.) +
+                       (bb[:, 2] - bb[:, 0] + 1.) * (bb[:, 3] - bb[:, 1] + 1.) - inters)
+                if np.max(inters / uni) > ovthresh:
+                    bok = True
+            if bok:
+                nok += 1
+    # TP / FP / FROC marking :206-247
+    nd = len(image_ids)
+    tp = np.zeros(nd)
+    fp = np.zeros(nd)
+    fp_froc = np.zeros(nd)
+    for d in range(nd):
+        R = class_recs[image_ids[d]]
+        bb = BB[d, :]
+        ovmax = -np.inf
+        BBGT = R['bbox']
+        if BBGT.size > 0:
+            ixmin = np.maximum(BBGT[:, 0], bb[0])
+            iymin = np.maximum(BBGT[:, 1], bb[1])
+            ixmax = np.minimum(BBGT[:, 2], bb[2])
+            iymax = np.minimum(BBGT[:, 3], bb[3])
+            iw = np.maximum(ixmax - ixmin + 1., 0.)
+            ih = np.maximum(iymax - iymin + 1., 0.)
+            inters = iw * ih
+            uni = ((bb[2] - bb[0] + 1.) * (bb[3] - bb[1] + 1.) +
+                   (BBGT[:, 2] - BBGT[:, 0] + 1.) * (BBGT[:, 3] - BBGT[:, 1] + 1.) - inters)
+            overlaps = inters / uni
+            ovmax = np.max(overlaps)
+            jmax = np.argmax(overlaps)
+        if ovmax > ovthresh:
+            if not R['difficult'][jmax]:
+                if not R['det'][jmax]:
+                    tp[d] = 1.
+                    R['det'][jmax] = 1
+                else:
+                    fp[d] = 1.
+        else:
+            fp[d] = 1.
+        if sorted_scores[d] <= -score_thresh:
+            if ovmax <= ovthresh:
+                fp_froc[d] = 1.
+    num_all_fps = np.sum(fp_froc)
+    num_fp_per_img = [int(np.sum(fp_froc[image_ids == i])) for i in range(n_images)]   # :252-262
+    fp = np.cumsum(fp)                                                                   # :265-271
+    tp = np.cumsum(tp)
+    rec = tp / float(npos)
+    prec = tp / np.maximum(tp + fp, np.finfo(np.float64).eps)
+    ap = voc_ap(rec, prec, use_07_metric)
+    return rec, prec, ap, ni, nok, num_all_fps, num_fp_per_img

@@ -214,6 +214,33 @@ def main():
                     t0 = time.perf_counter()
                     fn(bn, qn)
                     emit(out, op="cpu_bbox_overlaps", N=n, K=k, ms=(time.perf_counter() - t0) * 1e3)
+    if want("train"):
+        # BASELINE config C2: the device kernels of one training step, chained on one stream
+        # with no host synchronisation (anchor labels -> proposals 2000 pre-NMS -> RoI x GT IoU
+        # -> 128 RoIs per image -> roi_pool fwd + bwd).  The reference's npr.choice sampling
+        # stays on the host in the product path; here the first 128 proposals stand in for it.
+        from wssdl_bus_b200.rpn_msr.generate_anchors import generate_anchors
+        base = generate_anchors()
+        for B in (1, 16):
+            feat = torch.from_numpy(syn.feature_map(1, B, 38, 50, 512)).cuda()
+            cls, reg, info = [torch.from_numpy(v).cuda() for v in syn.rpn_outputs(7, B, 38, 50, 9)]
+            gt, num = [torch.from_numpy(v).cuda() for v in syn.gt_boxes(9, B)]
+            gt64 = gt[:, :, :4].double().contiguous()
+            gtop = torch.randn((B * 128, 7, 7, 512), device="cuda")
+            pick = (torch.arange(B, device="cuda")[:, None] * 2000 + torch.arange(128, device="cuda")[None]).reshape(-1)
+
+            def step():
+                ops.anchor_labels(gt, num, info, 38, 50, base, 16)
+                p = ops.proposals(cls, reg, info, base, 16, 2000, 2000, 0.7, 16)
+                r = p["rois"]
+                for b in range(B):
+                    ops.bbox_overlaps_device(r[b * 2000:(b + 1) * 2000, 1:5].double(), gt64[b], ops.IOU, torch.float64)
+                rr = r[pick].contiguous()
+                top, arg = ops.roi_pool_forward(feat, rr, 7, 7, 1 / 16.)
+                ops.roi_pool_backward((B, 38, 50, 512), rr, arg, gtop, 7, 7, 1 / 16.)
+            med, best = timeit(step, iters=10, flush=False)
+            emit(out, op="train_step_device_kernels", tag="C2 2000 pre-NMS, 128 RoIs/image, fwd+bwd", B=B,
+                 ms=med, ms_min=best, images_per_s=B / med * 1e3)
     if want("detect"):
         for B in (1, 256):
             S, K = 300, 3

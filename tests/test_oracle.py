@@ -224,3 +224,23 @@ def test_detections_postprocess_restatement_properties(oracle_mod):
     agn = oracle_mod.layers.detections_postprocess(scores, pb, max_per_image=0, cls_agnostic_nms=True)
     for j in range(1, K):
         assert set(map(tuple, agn[j])) <= set(map(tuple, base[j]))
+
+
+def test_voc_eval_restatement_hand_cases(oracle_mod):
+    """datasets/voc_eval_bus.py:143-275 restated (no fixtures in the reference): a duplicate
+    detection is an FP, a match to a difficult box is ignored, AP07 of a perfect ranking is 1."""
+    L = oracle_mod.layers
+    gt = [np.array([[10, 10, 50, 50]]), np.array([[0, 0, 20, 20]])]
+    dif = [np.array([False]), np.array([True])]
+    rec, prec, ap, ni, nok, nfp, per_img = L.voc_eval_arrays(
+        [0, 0, 1, 1], [0.9, 0.8, 0.7, 0.3],
+        [[10, 10, 50, 50], [12, 12, 50, 50], [0, 0, 20, 20], [100, 100, 120, 120]], gt, dif,
+        use_07_metric=True)
+    assert rec.tolist() == [1, 1, 1, 1] and np.allclose(prec, [1, .5, .5, 1 / 3.])
+    assert abs(ap - 1.0) < 1e-12 and (ni, nok, nfp, per_img) == (2, 2, 0, [0, 0])
+    # a confident miss is a FROC false positive of its image; CorLoc drops
+    rec, prec, ap, ni, nok, nfp, per_img = L.voc_eval_arrays(
+        [0], [0.95], [[200, 200, 260, 260]], gt, dif, use_07_metric=False)
+    assert (ni, nok, nfp, per_img) == (2, 0, 1, [1, 0]) and ap == 0
+    assert L.voc_eval_arrays([], [], np.zeros((0, 4)), gt, dif)[2] == -1
+    assert abs(L.voc_ap(np.array([.5, 1.]), np.array([1., .5]), False) - 0.75) < 1e-12

@@ -42,6 +42,8 @@ SIGNATURES = {
                              _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wssdl_detect_postprocess": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _d, _i, _i, _vp, _vp,
                                       _vp, _vp, _vp]),
+    "wssdl_eval_match": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _d, _f, _vp, _vp, _vp, _vp, _vp,
+                              _vp]),
     "wssdl_anchor_labels_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "wssdl_anchor_labels": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _d, _d, _i,
                                  _vp, _vp, _vp, _vp, _sz, _vp]),

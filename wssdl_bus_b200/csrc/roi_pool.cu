@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
 roi_pool_fwd_tiled_kernel(const float* __restrict__ bottom, const float* __restrict__ rois,
                           const int* __restrict__ perm, const int* __restrict__ img_start,
                           int B, int H, int W, int C, int R, int PH, int PW,
-                          float spatial_scale, int RB, FastDiv divPW, const Ones ones,
+                          float spatial_scale, int RB, FastDiv divPW, const Ones ones_p,
                           float* __restrict__ top, int* __restrict__ argmax) {
   extern __shared__ __align__(16) unsigned char t_smem[];
   __shared__ int s_count, s_next;
@@ -383,6 +383,17 @@ roi_pool_fwd_tiled_kernel(const float* __restrict__ bottom, const float* __restr
   }
   bool staged = false;
 
+  // The unit operands of upd_fma must live in ordinary registers: as kernel-parameter
+  // (constant bank) operands ptxas re-loads them with four LDCUs in every trip of the cell
+  // loop, and a plain copy is folded away again.  A round trip through shared memory is
+  // opaque to it.
+  __shared__ Ones s_ones;
+  if (tid == 0) s_ones = ones_p;
+  __syncthreads();
+  Ones ones;
+  ones.f = *reinterpret_cast<volatile float*>(&s_ones.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ones.i[k] = *reinterpret_cast<volatile int*>(&s_ones.i[k]);
   const int lane32 = tid & 31;
   const int WC = W * C;
   const size_t ph_stride = (size_t)PW * C;          // output elements between ph and ph+1

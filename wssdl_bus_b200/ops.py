@@ -449,3 +449,39 @@ def detect_postprocess(rois, scores, bbox_pred, im_meta, roi_counts=None, roi_st
     if want_pred_boxes:
         out["pred_boxes"] = pred
     return out
+
+
+# ------------------------------------------------------------------ evaluation: detection matching
+def eval_match(dets, det_counts, gt_boxes, num_gt, difficult=None, ovthresh=0.5, score_thresh=0.5):
+    """Per-detection TP / FP / FROC flags and per-image CorLoc flags (voc_eval_bus.py:161-247)
+    for the blob of detect_postprocess.  dets [B,K,S,5], det_counts [B,K], gt_boxes [B,G,5]
+    (x1,y1,x2,y2,cls), num_gt [B], difficult [B,G] bool/u8 or None.  Returns dict of device
+    tensors: tp, fp, fp_froc [B,K,S] u8, img_stats [B,K,2] i32, npos [K] i32."""
+    dets = _cuda(dets, torch.float32)
+    dev = dets.device
+    det_counts = _cuda(det_counts, torch.int32, dev)
+    gt_boxes = _cuda(gt_boxes, torch.float32, dev)
+    num_gt = _cuda(num_gt, torch.int32, dev)
+    if dets.dim() != 4 or dets.shape[3] != 5 or gt_boxes.dim() != 3 or gt_boxes.shape[2] != 5:
+        raise ValueError("dets [B,K,S,5], gt_boxes [B,G,5]")
+    B, K, S, _ = dets.shape
+    G = gt_boxes.shape[1]
+    if tuple(det_counts.shape) != (B, K) or gt_boxes.shape[0] != B or num_gt.shape[0] != B:
+        raise ValueError("det_counts [B,K], gt_boxes [B,G,5], num_gt [B]")
+    diff = _cuda(np.asarray(difficult, dtype=np.uint8) if isinstance(difficult, (list, np.ndarray))
+                 else difficult, torch.uint8, dev) if difficult is not None else None
+    if diff is not None and tuple(diff.shape) != (B, G):
+        raise ValueError("difficult [B,G]")
+    with torch.cuda.device(dev):
+        tp = torch.zeros((B, K, S), dtype=torch.uint8, device=dev)
+        fp = torch.zeros_like(tp)
+        ff = torch.zeros_like(tp)
+        stats = torch.zeros((B, K, 2), dtype=torch.int32, device=dev)
+        npos = torch.zeros((K,), dtype=torch.int32, device=dev)
+        rc = _lib.lib().wssdl_eval_match(_ptr(dets), _vp(det_counts.data_ptr()), B, K, S,
+                                         _ptr(gt_boxes), _vp(num_gt.data_ptr()), _ptr(diff), G,
+                                         float(ovthresh), float(score_thresh), _vp(tp.data_ptr()),
+                                         _vp(fp.data_ptr()), _vp(ff.data_ptr()),
+                                         _vp(stats.data_ptr()), _vp(npos.data_ptr()), _stream(dev))
+    _lib.check(rc, "wssdl_eval_match")
+    return dict(tp=tp, fp=fp, fp_froc=ff, img_stats=stats, npos=npos)
