@@ -228,3 +228,30 @@ def test_c3_resnet_shapes_properties(oracle_mod):
     assert abs(float(gb.double().sum()) - float((arg >= 0).sum())) < 1e-3 * float((arg >= 0).sum())
     gd = ops.roi_pool_backward((B, H, W, C), rois, arg, g, 14, 14, c["scale"], deterministic=True)
     np.testing.assert_allclose(gb.cpu().numpy(), gd.cpu().numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_fwd_random_shape_sweep_both_kernels(oracle_mod, monkeypatch):
+    """Seeded sweep over map sizes, channel counts, pooled sizes, scales and RoI counts (incl.
+    PH != PW, maps that barely fit / do not fit the shared-memory slice, C = 16, single RoIs):
+    direct and tiled kernels against the oracle, both bin modes."""
+    rng = np.random.default_rng(2024)
+    for trial in range(24):
+        B = int(rng.integers(1, 5))
+        H, W = int(rng.integers(3, 61)), int(rng.integers(3, 61))
+        C = int(rng.choice([16, 32, 48, 64, 80, 128, 20, 7]))
+        PH, PW = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        stride = int(rng.choice([4, 8, 16, 32]))
+        R = int(rng.choice([1, 2, 17, 100, 333]))
+        bottom = syn.feature_map(500 + trial, B, H, W, C)
+        rois = syn.rois_for_pool(600 + trial, R, B, im_w=W * stride, im_h=H * stride)
+        if trial % 5 == 0:                       # a few boxes hanging over the border
+            rois[: max(1, R // 4), 3:5] += 3 * stride
+        mode = "cpu" if trial % 2 == 0 else "gpu"
+        want_top, want_arg = oracle_mod.clib.roi_pool_fwd(bottom, rois, PH, PW, 1.0 / stride,
+                                                          bin_mode=0 if mode == "cpu" else 1)
+        for kern in ("direct", "tiled"):
+            monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
+            top, arg = ops.roi_pool_forward(bottom, rois, PH, PW, 1.0 / stride, bin_mode=mode)
+            ctx = (trial, kern, B, H, W, C, PH, PW, stride, R, mode)
+            assert np.array_equal(arg.cpu().numpy(), want_arg), ctx
+            assert np.array_equal(top.cpu().numpy(), want_top), ctx
