@@ -112,7 +112,7 @@ def main():
         r256 = realistic_rois(256)
         ru = torch.from_numpy(syn.rois_for_pool(5, 16 * 300, 16)).cuda()
         ru = ru[torch.argsort(ru[:, 0], stable=True)].contiguous()
-        for kern, st in (("direct", "1"), ("tiled", "1"), ("tiled", "0")):
+        for kern, st in (("direct", "1"), ("tiled", "1"), ("band", "1")):
             os.environ["WSSDL_ROI_FWD_KERNEL"] = kern
             os.environ["WSSDL_ROI_FWD_STREAM_ST"] = st
             tag = "[%s st=%s] " % (kern, st)

@@ -53,7 +53,7 @@ def test_c4_full_batch_properties_and_kernel_agreement(oracle_mod, monkeypatch):
     step): the oracle checks a sample of images end to end; the whole batch is checked through
     size-independent properties (every image keeps 300 RoIs in descending-score order, RoIs are
     clipped and at least min_size wide, top == bottom[argmax], argmax channel == output
-    channel) and by the two forward kernels agreeing bit for bit."""
+    channel) and by the three forward kernels agreeing bit for bit."""
     B = 256
     feat, cls, reg, info = _inputs(7000, B)
     x = torch.from_numpy(feat).cuda()
@@ -88,6 +88,8 @@ def test_c4_full_batch_properties_and_kernel_agreement(oracle_mod, monkeypatch):
         assert np.array_equal(top[b * 300:(b + 1) * 300].cpu().numpy(), wt)
         assert np.array_equal(arg[b * 300:(b + 1) * 300].cpu().numpy(), wa)
     # the shared-memory kernel (counting-sort pre-pass, workspace) gives the same bytes
-    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", "tiled")
-    top2, arg2 = ops.roi_pool_forward(x, r, 7, 7, 1 / 16.)
-    assert torch.equal(top2, top) and torch.equal(arg2, arg)
+    for kern in ("tiled", "band"):
+        monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
+        top2, arg2 = ops.roi_pool_forward(x, r, 7, 7, 1 / 16.)
+        assert torch.equal(top2, top) and torch.equal(arg2, arg), kern
+        del top2, arg2

@@ -13,11 +13,12 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-5
 
 
-@pytest.fixture(params=["direct", "tiled"])
+@pytest.fixture(params=["direct", "tiled", "band"])
 def fwd_kernel(request, monkeypatch):
-    """Forces one of the two forward kernels (roi_pool.cu: direct = one CTA per output row
-    reading L2; tiled = shared-memory resident channel slice).  Shapes the tiled kernel
-    does not take (C % 16 != 0, misaligned pointers) fall through to the direct one."""
+    """Forces one of the three forward kernels (roi_pool.cu: direct = one CTA per output row
+    reading L2; tiled = shared-memory resident 16-channel slice of the whole map; band =
+    32-channel slice of overlapping row bands).  Shapes a shared-memory kernel does not take
+    (C % 16 / 32 != 0, misaligned pointers) fall through to the direct one."""
     monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", request.param)
     return request.param
 
@@ -73,11 +74,12 @@ def test_fwd_misaligned_pointer_uses_scalar_kernel(oracle_mod):
     assert np.array_equal(top.cpu().numpy(), wt) and np.array_equal(arg.cpu().numpy(), wa)
 
 
+@pytest.mark.parametrize("kern", ["tiled", "band"])
 @pytest.mark.parametrize("mode", ["cpu", "gpu"])
-def test_fwd_tiled_sorted_lists_many_images(oracle_mod, mode, monkeypatch):
-    """R > 4096: the tiled kernel takes its per-image RoI lists from the counting-sort
+def test_fwd_tiled_sorted_lists_many_images(oracle_mod, mode, kern, monkeypatch):
+    """R > 4096: the shared-memory kernels take their per-image RoI lists from the counting-sort
     pre-pass in the workspace.  Batch indices are shuffled and some are out of range."""
-    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", "tiled")
+    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
     B, H, W, C = 24, 38, 50, 32
     bottom = syn.feature_map(30, B, H, W, C)
     rois = np.concatenate([syn.rois_for_pool(31, 5000, B), syn.adversarial_rois(B, W, H)])
@@ -99,12 +101,13 @@ def test_fwd_tiled_sorted_lists_many_images(oracle_mod, mode, monkeypatch):
     assert np.array_equal(t2.cpu().numpy(), t) and np.array_equal(a2.cpu().numpy(), a)
 
 
+@pytest.mark.parametrize("kern,C", [("tiled", 48), ("band", 64)])
 @pytest.mark.parametrize("B,R", [(1, 300), (2, 700), (3, 40), (5, 4096), (1, 1)])
-def test_fwd_tiled_chunked_scan_lists(oracle_mod, B, R, monkeypatch):
+def test_fwd_tiled_chunked_scan_lists(oracle_mod, B, R, kern, C, monkeypatch):
     """R <= 4096: RoI lists are built inside each CTA; few images split their RoIs over
     several CTAs (chunk = RoI index mod nchunks).  Also without argmax."""
-    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", "tiled")
-    H, W, C = 38, 50, 48
+    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
+    H, W = 38, 50
     bottom = syn.feature_map(33, B, H, W, C)
     rois = syn.rois_for_pool(34, R, B)
     wt, wa, t, a = _fwd_both(oracle_mod, bottom, rois, 7, 7, 1 / 16., "cpu")
@@ -230,10 +233,34 @@ def test_c3_resnet_shapes_properties(oracle_mod):
     np.testing.assert_allclose(gb.cpu().numpy(), gd.cpu().numpy(), rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("mode", ["cpu", "gpu"])
+def test_fwd_band_bins_taller_than_the_overlap(oracle_mod, mode, monkeypatch):
+    """Band kernel: a 38x50 map is held as two overlapping row bands.  RoIs several times
+    taller than the map have bins that no band holds completely: those take the kernel's
+    global-memory path.  Mixed with ordinary RoIs, RoIs whose bins all belong to one band,
+    and RoIs that start far above / end far below the map."""
+    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", "band")
+    B, H, W, C = 3, 38, 50, 96
+    bottom = syn.feature_map(40, B, H, W, C)
+    rng = np.random.default_rng(41)
+    tall = []
+    for i in range(60):
+        x1 = rng.integers(-200, 700)
+        y1 = rng.integers(-2500, 500)
+        tall.append([i % B, x1, y1, x1 + rng.integers(16, 900), y1 + rng.integers(700, 4000)])
+    top_only = [[b, 10, 0, 400, 150] for b in range(B)]        # rows 0..9: band 0 only
+    bot_only = [[b, 300, 400, 790, 599] for b in range(B)]     # rows 25..37: band 1 only
+    rois = np.concatenate([np.array(tall + top_only + bot_only, np.float32),
+                           syn.rois_for_pool(42, 200, B), syn.adversarial_rois(B, W, H)])
+    for PH, PW in ((7, 7), (2, 3), (14, 14)):
+        wt, wa, t, a = _fwd_both(oracle_mod, bottom, rois, PH, PW, 1 / 16., mode)
+        assert np.array_equal(a, wa) and np.array_equal(t, wt), (PH, PW)
+
+
 def test_fwd_random_shape_sweep_both_kernels(oracle_mod, monkeypatch):
     """Seeded sweep over map sizes, channel counts, pooled sizes, scales and RoI counts (incl.
     PH != PW, maps that barely fit / do not fit the shared-memory slice, C = 16, single RoIs):
-    direct and tiled kernels against the oracle, both bin modes."""
+    direct, tiled and band kernels against the oracle, both bin modes."""
     rng = np.random.default_rng(2024)
     for trial in range(24):
         B = int(rng.integers(1, 5))
@@ -249,7 +276,7 @@ def test_fwd_random_shape_sweep_both_kernels(oracle_mod, monkeypatch):
         mode = "cpu" if trial % 2 == 0 else "gpu"
         want_top, want_arg = oracle_mod.clib.roi_pool_fwd(bottom, rois, PH, PW, 1.0 / stride,
                                                           bin_mode=0 if mode == "cpu" else 1)
-        for kern in ("direct", "tiled"):
+        for kern in ("direct", "tiled", "band"):
             monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
             top, arg = ops.roi_pool_forward(bottom, rois, PH, PW, 1.0 / stride, bin_mode=mode)
             ctx = (trial, kern, B, H, W, C, PH, PW, stride, R, mode)

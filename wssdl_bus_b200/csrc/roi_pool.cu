@@ -521,6 +521,308 @@ roi_pool_fwd_tiled_kernel(const float* __restrict__ bottom, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------
+// Forward, shared-memory resident 32-channel slice of a BAND of map rows ("band").
+//
+// What bounded the tiled kernel above (ncu, profiles/r01_ncu_roi_fwd_tiled.txt: LSU data pipe
+// 81 %, issue 75 %) follows from its 64 B cells: the four bin columns of a quarter warp land
+// in the same banks 1.5x per LDS.128 and a bin column leaves as a 64 B half line, i.e. one
+// LSU wavefront per 64 B.  A 32-channel slice makes a cell exactly one 128 B bank row:
+//   - four lanes share a bin column, 32 B (8 channels) each; a quarter warp holds two
+//     columns A and B; A reads chunks (2j, 2j+1) and B reads (2j+1, 2j) of their cells, so
+//     each LDS.128 phase touches all eight 16 B bank groups once WHATEVER the two cells
+//     are: conflict-free by construction, 128 B per wavefront;
+//   - the four lanes of a column store 4 x 32 B = one full 128 B line per STG.256 wavefront,
+//     half the store wavefronts of the 64 B layout.  The A/B register roles differ, so the
+//     store is the one divergent statement (two half-populated STG.256, same wavefronts)
+//     instead of 16 selects per bin.
+// 38x50 cells x 128 B = 243 KB does not fit 227 KB, so the map is cut into NB bands of Hb
+// rows that overlap by `ov` rows (ov >= the tallest bin a RoI inside the map can have): band
+// b holds rows [b*step, b*step + Hb), step = Hb - ov, and OWNS the bins whose first row
+// falls into [b*step, (b+1)*step) (the last band: all the rest).  An owned bin of height
+// <= ov lies inside the band; taller ones (RoIs far larger than the map) take a slow path
+// that reads global memory.  Every bin is written by exactly one CTA; RoIs that own no bin
+// in a band are dropped from that CTA's list.  For 38x50, 7x7: 2 bands of 23 rows (147 KB),
+// the map is staged 1.21x.
+constexpr int B_SLICE = 32;             // channels per CTA: one cell = 128 B = all 32 banks
+constexpr int B_LANES = B_SLICE / 4;    // float4 chunks per cell
+constexpr int B_THREADS = 1024;
+constexpr int B_SCAN_MAX_R = 4096;
+constexpr int B_MAX_RB = 1024;
+
+// One bin whose rows are not all resident in this band: pooled straight from global memory.
+// Rare (RoIs several times taller than the map), so it is kept out of line.
+template <bool HAS_ARGMAX>
+__device__ __noinline__ void band_slow_bin(const float* __restrict__ img_base, int hs, int he,
+                                           int ws, int nw, int W, int C, int c_lo,
+                                           float* __restrict__ top_o, int* __restrict__ arg_o) {
+  float m[8];
+  int mi[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { m[k] = -FLT_MAX; mi[k] = -1; }
+  for (int h = hs; h < he; ++h)
+    for (int w = ws; w < ws + nw; ++w) {
+      const int cell = (h * W + w) * C + c_lo;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(img_base + cell));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(img_base + cell + 4));
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (v[k] > m[k]) { m[k] = v[k]; mi[k] = cell + k; }
+    }
+  st256<true>(top_o, make_float4(m[0], m[1], m[2], m[3]), make_float4(m[4], m[5], m[6], m[7]));
+  if (HAS_ARGMAX)
+    st256<true>(arg_o, make_int4(mi[0], mi[1], mi[2], mi[3]), make_int4(mi[4], mi[5], mi[6], mi[7]));
+}
+
+struct BandGeom {
+  int NB, Hb, step;   // bands per image, rows per band, first-row distance of two bands
+};
+
+template <int BIN_MODE, bool HAS_ARGMAX, bool LINEAR>
+__global__ void __launch_bounds__(B_THREADS, 1)
+roi_pool_fwd_band_kernel(const float* __restrict__ bottom, const float* __restrict__ rois,
+                         const int* __restrict__ perm, const int* __restrict__ img_start,
+                         int B, int H, int W, int C, int R, int PH, int PW,
+                         float spatial_scale, int RB, int nchunks, BandGeom bg, FastDiv divPW,
+                         const Ones ones_p, float* __restrict__ top, int* __restrict__ argmax) {
+  extern __shared__ __align__(128) unsigned char b_smem[];
+  __shared__ int s_count, s_next, s_active;
+  __shared__ int s_hist[T_CLASSES], s_start[T_CLASSES];
+  __shared__ Ones s_ones;
+  const int tid = threadIdx.x;
+  const int slice = blockIdx.x;
+  const int band = blockIdx.y % bg.NB, chunk = blockIdx.y / bg.NB;
+  const int img = blockIdx.z;                       // == B: RoIs with no valid image
+  const bool valid_img = img < B;
+  if (!valid_img && band != 0) return;              // their (empty) bins all start at row 0
+  const int row0 = band * bg.step;                  // first resident row
+  const int row1 = min(row0 + bg.Hb, H);            // one past the last resident row
+  const int nrows = row1 - row0;
+
+  // cells must be 128 B aligned (the xor-16 chunk pairing and the conflict-free phases rely
+  // on it); the launch reserves 128 spare bytes in case the dynamic segment is not
+  const unsigned raw_u32 = (unsigned)__cvta_generic_to_shared(b_smem);
+  float4* s_map = reinterpret_cast<float4*>(b_smem + ((128u - (raw_u32 & 127u)) & 127u));
+  unsigned* s_he = reinterpret_cast<unsigned*>(s_map + (size_t)bg.Hb * W * B_LANES);  // hs | he<<16
+  unsigned* s_we = s_he + RB * PH;                                                   // ws | we<<16
+  int* s_n = reinterpret_cast<int*>(s_we + RB * PW);     // RoI index in the caller's array
+  int* s_pr = s_n + RB;                                  // owned bins: ph_lo | ph_hi<<8 | class<<16
+  int* s_order = s_pr + RB;                              // RoIs with work here, heaviest class first
+  int* s_list = s_order + RB;                            // scan mode only
+
+  // ---- this CTA's RoIs (as in the tiled kernel)
+  const int* list;
+  int r_begin, r_end;
+  if (perm != nullptr) {
+    const int a = img_start[img];
+    const int n_img = img_start[img + 1] - a;
+    list = perm + a;
+    r_begin = (int)((long long)n_img * chunk / nchunks);
+    r_end = (int)((long long)n_img * (chunk + 1) / nchunks);
+  } else {
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int r = tid; r < R; r += blockDim.x)
+      if (r % nchunks == chunk && roi_bucket(__ldg(rois + (size_t)r * 5), B) == img)
+        s_list[atomicAdd(&s_count, 1)] = r;
+    __syncthreads();
+    list = s_list;
+    r_begin = 0;
+    r_end = s_count;
+  }
+  if (r_end <= r_begin) return;
+
+  // ---- stage this band's rows of the channel slice: 128 contiguous bytes per cell
+  if (valid_img) {
+    const int CV = C >> 2;
+    const float4* src = reinterpret_cast<const float4*>(bottom + ((size_t)img * H + row0) * W * C) +
+                        slice * B_LANES;
+    const int n4 = nrows * W * B_LANES;
+    for (int i = tid; i < n4; i += blockDim.x)
+      cp_async16(s_map + i, src + (size_t)(i >> 3) * CV + (i & 7));
+  }
+  bool staged = false;
+
+  if (tid == 0) s_ones = ones_p;                    // see the tiled kernel: opaque unit operands
+  __syncthreads();
+  Ones ones;
+  ones.f = *reinterpret_cast<volatile float*>(&s_ones.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ones.i[k] = *reinterpret_cast<volatile int*>(&s_ones.i[k]);
+  const int lane32 = tid & 31;
+  const int WC = W * C;
+  const size_t ph_stride = (size_t)PW * C;          // output elements between ph and ph+1
+  const float* img_base = bottom + (size_t)(valid_img ? img : 0) * H * WC;
+  // per-thread constants: a warp always holds 8 whole columns, so the quarter j and the
+  // column role sw of a lane never change
+  const int j = lane32 & 3;                         // channels [8j, 8j+8) of the slice
+  const int sw = (lane32 >> 2) & 1;                 // column A (0) or B (1) of its quarter warp
+  const int c_thr = slice * B_SLICE + j * 8;
+  // registers m[0..3] hold chunk 2j+sw, m[4..7] chunk 2j+1-sw
+  const int c_a = c_thr + 4 * sw, c_b = c_thr + 4 * (1 - sw);
+  const unsigned row_bytes = (unsigned)W * 128u;    // one resident row
+  const unsigned map_u32 = (unsigned)__cvta_generic_to_shared(s_map);
+  // shared address of chunk A of cell (h, w): map_a + h*row_bytes + w*128
+  const unsigned map_a = map_u32 + (unsigned)(2 * j + sw) * 16u - (unsigned)row0 * row_bytes;
+  // LINEAR: flat index of the cell whose chunk A sits at q is q*kmul + lin0 (kmul = C/128)
+  const int lin0 = -(int)(map_a * (unsigned)(C >> 7));
+
+  for (int r0 = r_begin; r0 < r_end; r0 += RB) {
+    const int nb = min(RB, r_end - r0);
+    __syncthreads();                                // previous batch fully consumed
+    if (tid == 0) { s_next = 0; s_active = 0; }
+    if (tid < T_CLASSES) s_hist[tid] = 0;
+    __syncthreads();
+    for (int rl = tid; rl < nb; rl += blockDim.x) {
+      const int n = list[r0 + rl];
+      s_n[rl] = n;
+      const RoiCells g = roi_cells(rois + (size_t)n * 5, spatial_scale, PH, PW);
+      int max_nw = 0;
+      for (int pw = 0; pw < PW; ++pw) {
+        int ws = min(max(bin_lo<BIN_MODE>(pw, g.bin_w) + g.start_w, 0), W);   // cc:167-176
+        int we = min(max(bin_hi<BIN_MODE>(pw, g.bin_w) + g.start_w, 0), W);
+        if (!valid_img) ws = we = 0;
+        s_we[rl * PW + pw] = (unsigned)ws | ((unsigned)we << 16);
+        max_nw = max(max_nw, we - ws);
+      }
+      int max_nh = 0, ph_lo = PH, ph_hi = 0;
+      for (int ph = 0; ph < PH; ++ph) {
+        int hs = min(max(bin_lo<BIN_MODE>(ph, g.bin_h) + g.start_h, 0), H);
+        int he = min(max(bin_hi<BIN_MODE>(ph, g.bin_h) + g.start_h, 0), H);
+        if (!valid_img) hs = he = 0;
+        s_he[rl * PH + ph] = (unsigned)hs | ((unsigned)he << 16);
+        // hs is non-decreasing in ph, so the bins a band owns are a contiguous range
+        const int owner = min(hs / bg.step, bg.NB - 1);
+        if (owner == band) {
+          ph_lo = min(ph_lo, ph);
+          ph_hi = ph + 1;
+          max_nh = max(max_nh, he - hs);
+        }
+      }
+      // cost class: lanes of a warp run in lock step over ph, so RoIs that share a warp
+      // should have the same rows-per-bin and cells-per-row
+      const int cls = min(max_nh, 7) * 8 + min(max_nw, 7);
+      s_pr[rl] = ph_lo | (ph_hi << 8) | (cls << 16);
+      if (ph_hi > ph_lo) atomicAdd(&s_hist[cls], 1);
+    }
+    if (!staged) { cp_async_wait_all(); staged = true; }
+    __syncthreads();
+    if (tid < T_CLASSES) {                          // counting sort by class, heaviest first
+      int before = 0;
+      for (int k = tid + 1; k < T_CLASSES; ++k) before += s_hist[k];
+      s_start[tid] = before;
+      if (tid == 0) s_active = before + s_hist[0];
+    }
+    __syncthreads();
+    for (int rl = tid; rl < nb; rl += blockDim.x) {
+      const int pr = s_pr[rl];
+      if (((pr >> 8) & 255) > (pr & 255)) s_order[atomicAdd(&s_start[pr >> 16], 1)] = rl;
+    }
+    __syncthreads();
+
+    // One work item = (RoI, pw, quarter of the slice): the thread walks the owned ph range
+    // down its bin column.  Warps draw 32 items (8 columns) at a time from a shared counter.
+    // The loop nest is written for instruction count (ncu source counters of the first
+    // version: 33 instructions per cell, 16 per bin row, 94 per bin):
+    //   - shared memory is addressed with 32-bit window addresses (ld.shared), the chunk of
+    //     column B is the chunk of column A xor 16;
+    //   - LINEAR (C % 128 == 0): a cell's flat index is linear in its shared-memory address,
+    //     flat = q * (C/128) + const, so the conditional move records q * (C/128) (`ones.i`
+    //     then hold C/128) and no cell counter is carried through the loops;
+    //   - rows advance one pointer by a per-item skip, outputs by two running pointers.
+    const int items = s_active * PW * 4;
+    for (;;) {
+      int base = 0;
+      if (lane32 == 0) base = atomicAdd(&s_next, 32);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= items) break;
+      const int it = base + lane32;
+      if (it >= items) continue;
+      const int col = it >> 2;
+      const int rs = (int)fastdiv((unsigned)col, divPW);
+      const int pw = col - rs * PW;
+      const int rl = s_order[rs];
+      const unsigned ww = s_we[rl * PW + pw];
+      const int ws = ww & 0xffff, nw = (int)(ww >> 16) - ws;
+      const int pr = s_pr[rl];
+      const int ph_lo = pr & 255, ph_hi = (pr >> 8) & 255;
+      const unsigned* he_p = s_he + rl * PH + ph_lo;
+      const unsigned* he_end = s_he + rl * PH + ph_hi;
+      const size_t o = (((size_t)s_n[rl] * PH + ph_lo) * PW + pw) * C + c_thr;
+      float* top_p = top + o;
+      int* arg_p = argmax + (HAS_ARGMAX ? o : 0);
+      const unsigned col_a = map_a + (unsigned)ws * 128u;     // chunk A of (row0, ws)
+      const unsigned nw_bytes = (unsigned)nw * 128u;
+      const unsigned row_skip = row_bytes - nw_bytes;
+      // LINEAR: flat = q*kmul + lin0 + channel; else flat = cellC + channel
+      const int fin_a = (LINEAR ? lin0 : 0) + c_a, fin_b = (LINEAR ? lin0 : 0) + c_b;
+#pragma unroll 1
+      for (; he_p != he_end; ++he_p, top_p += ph_stride, arg_p += ph_stride) {
+        const unsigned hh = *he_p;
+        const int hs = hh & 0xffff, he = (int)(hh >> 16);
+        if (he <= hs || nw <= 0) {                  // empty bin: (0, -1), cc:180-182
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int4 n1 = make_int4(-1, -1, -1, -1);
+          st256<true>(top_p, z, z);
+          if (HAS_ARGMAX) st256<true>(arg_p, n1, n1);
+          continue;
+        }
+        if (he > row1) {                            // not resident: slow path (uniform in j)
+          band_slow_bin<HAS_ARGMAX>(img_base, hs, he, ws, nw, W, C, c_thr, top_p, arg_p);
+          continue;
+        }
+        float m[8];
+        int mi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          m[k] = -FLT_MAX;
+          mi[k] = -1 - (k < 4 ? fin_a + k : fin_b + k - 4);   // + fin at the end => -1 if never updated
+        }
+        unsigned q = col_a + (unsigned)hs * row_bytes;
+        int cellC = LINEAR ? 0 : hs * WC + ws * C;
+        int r = he - hs;
+#pragma unroll 1
+        do {
+          const unsigned q_end = q + nw_bytes;
+#pragma unroll 1
+          do {
+            float4 v0, v1;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(q));
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(q ^ 16u));
+            const int key = LINEAR ? (int)q : cellC;
+            upd_fma(v0.x, key, m[0], mi[0], ones.f, ones.i[0]);
+            upd_fma(v0.y, key, m[1], mi[1], ones.f, ones.i[1]);
+            upd_fma(v0.z, key, m[2], mi[2], ones.f, ones.i[2]);
+            upd_fma(v0.w, key, m[3], mi[3], ones.f, ones.i[3]);
+            upd_fma(v1.x, key, m[4], mi[4], ones.f, ones.i[4]);
+            upd_fma(v1.y, key, m[5], mi[5], ones.f, ones.i[5]);
+            upd_fma(v1.z, key, m[6], mi[6], ones.f, ones.i[6]);
+            upd_fma(v1.w, key, m[7], mi[7], ones.f, ones.i[7]);
+            q += 128u;
+            if (!LINEAR) cellC += C;
+          } while (q != q_end);
+          q += row_skip;
+          if (!LINEAR) cellC += WC - nw * C;
+        } while (--r > 0);
+        const float4 ta = make_float4(m[0], m[1], m[2], m[3]);
+        const float4 tb = make_float4(m[4], m[5], m[6], m[7]);
+        const int4 aa = make_int4(mi[0] + fin_a, mi[1] + fin_a + 1, mi[2] + fin_a + 2, mi[3] + fin_a + 3);
+        const int4 ab = make_int4(mi[4] + fin_b, mi[5] + fin_b + 1, mi[6] + fin_b + 2, mi[7] + fin_b + 3);
+        if (sw) {
+          st256<true>(top_p, tb, ta);
+          if (HAS_ARGMAX) st256<true>(arg_p, ab, aa);
+        } else {
+          st256<true>(top_p, ta, tb);
+          if (HAS_ARGMAX) st256<true>(arg_p, aa, ab);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Backward, atomic scatter.  One CTA per (roi, ph-slice).  The reference's gather
 // (roi_pooling_op.cc:400-455) adds top_diff[n,ph,pw,c] to bottom_diff[b,h,w,c] iff
 //   b == roi batch, (h,w) inside the rounded RoI (:415-419), ph in [phstart(h),phend(h)),
@@ -778,6 +1080,55 @@ TiledPlan plan_tiled(int B, int H, int W, int C, int R, int PH, int PW, bool vec
   return p;
 }
 
+// Shape test + launch geometry of the band forward kernel.
+struct BandPlan {
+  bool ok;
+  bool scan;
+  int RB, nchunks;
+  BandGeom g;
+  size_t smem;
+};
+
+BandPlan plan_band(int B, int H, int W, int C, int R, int PH, int PW, bool aligned,
+                   size_t workspace_bytes) {
+  BandPlan p = {false, false, 0, 1, {1, 0, 0}, 0};
+  if (!aligned || C % B_SLICE != 0 || H > 65535 || W > 65535 || B + 1 > 65535) return p;
+  if (PH <= 0 || PW <= 0 || PH > 255 || H <= 0 || W <= 0) return p;
+  p.scan = R <= B_SCAN_MAX_R;
+  if (!p.scan && workspace_bytes < tiled_workspace_bytes(B, R)) return p;
+  if (!p.scan && (size_t)(B + 1) * sizeof(int) > (size_t)T_DYN_SMEM_MAX) return p;   // bucket counters
+  const size_t row_bytes = (size_t)W * B_SLICE * sizeof(float);
+  const size_t list_bytes = p.scan ? sizeof(int) * (size_t)R : 0;
+  const size_t per_roi = sizeof(int) * ((size_t)PH + PW + 3);
+  const size_t budget = T_DYN_SMEM_MAX - 128;       // 128: alignment slack of the map
+  // room for the bin edges of a useful number of RoIs first, rows with what is left
+  const size_t rb_want = (size_t)(R < 16 ? 16 : (R < 512 ? R : 512));
+  if (list_bytes + per_roi * rb_want + row_bytes >= budget) return p;
+  const long long hb_max = (long long)((budget - list_bytes - per_roi * rb_want) / row_bytes);
+  // the tallest bin of a RoI that lies inside the map, +1 for GPU_CEIL's overlapping edges
+  const int ov = (H + 1 + PH - 1) / PH + 2;
+  if (hb_max >= H) {
+    p.g.NB = 1; p.g.Hb = H; p.g.step = H;
+  } else {
+    if (hb_max <= ov) return p;
+    p.g.NB = (int)((H - ov + (hb_max - ov) - 1) / (hb_max - ov));
+    p.g.step = (H - ov + p.g.NB - 1) / p.g.NB;
+    p.g.Hb = p.g.step + ov;
+  }
+  const size_t map_bytes = row_bytes * p.g.Hb;
+  size_t rb = (budget - map_bytes - list_bytes) / per_roi;
+  if (rb > (size_t)B_MAX_RB) rb = B_MAX_RB;
+  if (rb > (size_t)R) rb = R < 16 ? 16 : R;
+  p.RB = (int)rb;
+  p.smem = map_bytes + list_bytes + per_roi * p.RB + 128;
+  const long long base = (long long)(C / B_SLICE) * (B > 0 ? B : 1) * p.g.NB;
+  const int avg = R / (B > 0 ? B : 1);
+  while (base * p.nchunks * 2 <= WSSDL_NUM_SMS && avg / (p.nchunks * 2) >= 16) p.nchunks *= 2;
+  if ((long long)p.g.NB * p.nchunks > 65535) return p;
+  p.ok = true;
+  return p;
+}
+
 // Opt a kernel into 227 KB of dynamic shared memory once per device (the attribute is
 // per device; one process may drive several).
 template <typename K>
@@ -838,6 +1189,58 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
   // tiled while its grid fits one wave.
   const bool tiled_pays = tp.scan && (long long)(C / T_SLICE) * B * tp.nchunks <= WSSDL_NUM_SMS &&
                           PH * PW <= 64 && (long long)R * PH * PW * 2 >= (long long)B * H * W;
+  // The band kernel (128 B cells: conflict-free loads, full-line stores) takes the batched
+  // case: many RoIs per image re-reading a map that L2 would otherwise serve ~35x, bins
+  // small enough (7x7-like) that the direct kernel sits on the L2 cap.  WSSDL_ROI_FWD_KERNEL=band
+  // forces it.
+  const int band_env = (kenv && kenv[0] == 'b') ? 1 : 0;
+  const BandPlan bp = plan_band(B, H, W, C, R, PH, PW, vec4 && al32, workspace_bytes);
+  const bool band_pays = kernel_env == 0 && !tiled_pays && PH * PW <= 64 &&
+                         (long long)R * PH * PW >= 4ll * B * H * W && bp.g.NB <= 4;
+  if (bp.ok && (band_env || band_pays)) {
+    int* img_start = nullptr;
+    int* perm = nullptr;
+    if (!bp.scan) {
+      img_start = static_cast<int*>(workspace);
+      perm = img_start + (B + 2);
+      const int cache16 = ((size_t)(B + 1) * 4 + (size_t)R * 2 <= (size_t)T_DYN_SMEM_MAX) ? 1 : 0;
+      const size_t bsmem = (size_t)(B + 1) * 4 + (cache16 ? (size_t)R * 2 : 0);
+      static unsigned long long done_bb = 0;
+      WSSDL_RETURN_IF_CUDA(allow_big_smem(roi_bucket_kernel, &done_bb));
+      roi_bucket_kernel<<<1, 1024, bsmem, s>>>(rois, R, B, cache16, img_start, perm);
+      WSSDL_CHECK_LAUNCH();
+    }
+    const FastDiv dPW = make_fastdiv((unsigned)PW);
+    // C % 128 == 0: the argmax update records (shared address) * (C/128), see the kernel
+    const bool linear = (C % 128 == 0);
+    const int km = linear ? C / 128 : 1;
+    const Ones ones = {1.0f, {km, km, km, km, km, km, km, km}};
+    dim3 grid((unsigned)(C / B_SLICE), (unsigned)(bp.g.NB * bp.nchunks), (unsigned)(B + 1));
+#define LAUNCH_BAND(M, A, L)                                                                   \
+  do {                                                                                         \
+    static unsigned long long done_k = 0;                                                      \
+    WSSDL_RETURN_IF_CUDA(allow_big_smem(roi_pool_fwd_band_kernel<M, A, L>, &done_k));          \
+    roi_pool_fwd_band_kernel<M, A, L><<<grid, B_THREADS, bp.smem, s>>>(                        \
+        bottom, rois, perm, img_start, B, H, W, C, R, PH, PW, spatial_scale, bp.RB, bp.nchunks, \
+        bp.g, dPW, ones, top, argmax);                                                         \
+  } while (0)
+#define LAUNCH_BAND_A(M, A)                                                                    \
+  do {                                                                                         \
+    if (linear) LAUNCH_BAND(M, A, true);                                                       \
+    else LAUNCH_BAND(M, A, false);                                                             \
+  } while (0)
+    if (bin_mode == WSSDL_BIN_CPU_TRUNC) {
+      if (argmax) LAUNCH_BAND_A(WSSDL_BIN_CPU_TRUNC, true);
+      else LAUNCH_BAND_A(WSSDL_BIN_CPU_TRUNC, false);
+    } else {
+      if (argmax) LAUNCH_BAND_A(WSSDL_BIN_GPU_CEIL, true);
+      else LAUNCH_BAND_A(WSSDL_BIN_GPU_CEIL, false);
+    }
+#undef LAUNCH_BAND_A
+#undef LAUNCH_BAND
+    WSSDL_CHECK_LAUNCH();
+    return WSSDL_OK;
+  }
   if (tp.ok && kernel_env != 1 && (tiled_pays || kernel_env == 2)) {
     int* img_start = nullptr;
     int* perm = nullptr;
