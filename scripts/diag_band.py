@@ -20,8 +20,14 @@ rois = np.concatenate([np.array(tall + top_only + bot_only, np.float32),
 for mode in ("cpu", "gpu"):
     for PH, PW in ((7, 7), (2, 3), (14, 14)):
         wt, wa = oracle.clib.roi_pool_fwd(bottom, rois, PH, PW, 1 / 16., bin_mode=0 if mode == "cpu" else 1)
-        for kern in ("direct", "tiled", "band"):
+        for kern in ("band", "direct", "tiled"):
             os.environ["WSSDL_ROI_FWD_KERNEL"] = kern
+            # poison the blocks the caching allocator will hand out for top / argmax
+            import torch
+            pz = [torch.full((rois.shape[0], PH, PW, C), float("nan"), device="cuda"),
+                  torch.full((rois.shape[0], PH, PW, C), -7, device="cuda", dtype=torch.int32)]
+            torch.cuda.synchronize()
+            del pz
             t, a = ops.roi_pool_forward(bottom, rois, PH, PW, 1 / 16., bin_mode=mode)
             t, a = t.cpu().numpy(), a.cpu().numpy()
             bad = np.argwhere((a != wa) | ~((t == wt) | (np.isnan(t) & np.isnan(wt))))

@@ -16,7 +16,7 @@ for l in open('gpurun_out/microbench_roicmp.jsonl'):
         print('%-50s %8.4f ms %8.1f GB/s  %.3f of measured' % (d['tag'], d['ms'], d['gbs'], d['frac_measured']))
 PY
 if [ "${SKIP_NCU}" != "1" ]; then
-  WSSDL_ROI_FWD_KERNEL=band timeout 900 ncu --set full --clock-control none --import-source on -k regex:roi_pool_fwd_band -s 2 -c 1 \
+  WSSDL_ROI_FWD_KERNEL=${NCU_KERNEL:-band} timeout 900 ncu --set full --clock-control none --import-source on -k regex:roi_pool_fwd_band -s 2 -c 1 \
       -o gpurun_out/prof_roi_fwd_band -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_band.log 2>&1
   tail -3 gpurun_out/ncu_band.log
 fi

@@ -17,8 +17,9 @@ RTOL, ATOL = 1e-5, 1e-5
 def fwd_kernel(request, monkeypatch):
     """Forces one of the three forward kernels (roi_pool.cu: direct = one CTA per output row
     reading L2; tiled = shared-memory resident 16-channel slice of the whole map; band =
-    32-channel slice of overlapping row bands).  Shapes a shared-memory kernel does not take
-    (C % 16 / 32 != 0, misaligned pointers) fall through to the direct one."""
+    32-channel slice of overlapping row bands; C % 128 == 0 takes its linear-index variant).
+    Shapes a shared-memory kernel does not take (C % 16 / 32 != 0, misaligned pointers) fall
+    through to the direct one."""
     monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", request.param)
     return request.param
 
@@ -39,9 +40,10 @@ def test_fwd_c1_shapes_bit_exact(oracle_mod, mode, fwd_kernel):
     assert np.array_equal(t, wt) and np.array_equal(a, wa)
 
 
+@pytest.mark.parametrize("C", [64, 128])
 @pytest.mark.parametrize("mode", ["cpu", "gpu"])
-def test_fwd_adversarial_rois_bit_exact(oracle_mod, mode, fwd_kernel):
-    B, H, W, C = 2, 38, 50, 64
+def test_fwd_adversarial_rois_bit_exact(oracle_mod, mode, C, fwd_kernel):
+    B, H, W = 2, 38, 50
     bottom = syn.feature_map(2, B, H, W, C)
     bottom[0, 3:9, 4:11] = -np.inf                     # cells that can never win
     bottom[1, 0, 0, :] = np.nan                        # NaN never wins either
@@ -74,13 +76,13 @@ def test_fwd_misaligned_pointer_uses_scalar_kernel(oracle_mod):
     assert np.array_equal(top.cpu().numpy(), wt) and np.array_equal(arg.cpu().numpy(), wa)
 
 
-@pytest.mark.parametrize("kern", ["tiled", "band"])
+@pytest.mark.parametrize("kern,C", [("tiled", 32), ("band", 32), ("band", 128)])
 @pytest.mark.parametrize("mode", ["cpu", "gpu"])
-def test_fwd_tiled_sorted_lists_many_images(oracle_mod, mode, kern, monkeypatch):
+def test_fwd_tiled_sorted_lists_many_images(oracle_mod, mode, kern, C, monkeypatch):
     """R > 4096: the shared-memory kernels take their per-image RoI lists from the counting-sort
     pre-pass in the workspace.  Batch indices are shuffled and some are out of range."""
     monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
-    B, H, W, C = 24, 38, 50, 32
+    B, H, W = 24, 38, 50
     bottom = syn.feature_map(30, B, H, W, C)
     rois = np.concatenate([syn.rois_for_pool(31, 5000, B), syn.adversarial_rois(B, W, H)])
     rng = np.random.default_rng(32)
@@ -101,7 +103,7 @@ def test_fwd_tiled_sorted_lists_many_images(oracle_mod, mode, kern, monkeypatch)
     assert np.array_equal(t2.cpu().numpy(), t) and np.array_equal(a2.cpu().numpy(), a)
 
 
-@pytest.mark.parametrize("kern,C", [("tiled", 48), ("band", 64)])
+@pytest.mark.parametrize("kern,C", [("tiled", 48), ("band", 64), ("band", 128)])
 @pytest.mark.parametrize("B,R", [(1, 300), (2, 700), (3, 40), (5, 4096), (1, 1)])
 def test_fwd_tiled_chunked_scan_lists(oracle_mod, B, R, kern, C, monkeypatch):
     """R <= 4096: RoI lists are built inside each CTA; few images split their RoIs over
@@ -233,14 +235,15 @@ def test_c3_resnet_shapes_properties(oracle_mod):
     np.testing.assert_allclose(gb.cpu().numpy(), gd.cpu().numpy(), rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("kern,C", [("band", 96), ("band", 128)])
 @pytest.mark.parametrize("mode", ["cpu", "gpu"])
-def test_fwd_band_bins_taller_than_the_overlap(oracle_mod, mode, monkeypatch):
+def test_fwd_band_bins_taller_than_the_overlap(oracle_mod, mode, kern, C, monkeypatch):
     """Band kernel: a 38x50 map is held as two overlapping row bands.  RoIs several times
     taller than the map have bins that no band holds completely: those take the kernel's
     global-memory path.  Mixed with ordinary RoIs, RoIs whose bins all belong to one band,
     and RoIs that start far above / end far below the map."""
-    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", "band")
-    B, H, W, C = 3, 38, 50, 96
+    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
+    B, H, W = 3, 38, 50
     bottom = syn.feature_map(40, B, H, W, C)
     rng = np.random.default_rng(41)
     tall = []
@@ -265,7 +268,7 @@ def test_fwd_random_shape_sweep_both_kernels(oracle_mod, monkeypatch):
     for trial in range(24):
         B = int(rng.integers(1, 5))
         H, W = int(rng.integers(3, 61)), int(rng.integers(3, 61))
-        C = int(rng.choice([16, 32, 48, 64, 80, 128, 20, 7]))
+        C = int(rng.choice([16, 32, 48, 64, 80, 128, 20, 7, 256]))
         PH, PW = int(rng.integers(1, 9)), int(rng.integers(1, 9))
         stride = int(rng.choice([4, 8, 16, 32]))
         R = int(rng.choice([1, 2, 17, 100, 333]))

@@ -19,6 +19,7 @@
 //     the outputs, never re-read by this kernel, use st.global.cs so they do not evict
 //     the feature map from L2.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -569,9 +570,14 @@ __device__ __noinline__ void band_slow_bin(const float* __restrict__ img_base, i
       for (int k = 0; k < 8; ++k)
         if (v[k] > m[k]) { m[k] = v[k]; mi[k] = cell + k; }
     }
-  st256<true>(top_o, make_float4(m[0], m[1], m[2], m[3]), make_float4(m[4], m[5], m[6], m[7]));
-  if (HAS_ARGMAX)
-    st256<true>(arg_o, make_int4(mi[0], mi[1], mi[2], mi[3]), make_int4(mi[4], mi[5], mi[6], mi[7]));
+  // plain 128-bit stores: ptxas 12.9 narrows the st.v8 inline asm of st256 to a scalar store
+  // in some clones of this out-of-line function (seen in SASS; caught by the tall-RoI test)
+  __stcs(reinterpret_cast<float4*>(top_o), make_float4(m[0], m[1], m[2], m[3]));
+  __stcs(reinterpret_cast<float4*>(top_o) + 1, make_float4(m[4], m[5], m[6], m[7]));
+  if (HAS_ARGMAX) {
+    __stcs(reinterpret_cast<int4*>(arg_o), make_int4(mi[0], mi[1], mi[2], mi[3]));
+    __stcs(reinterpret_cast<int4*>(arg_o) + 1, make_int4(mi[4], mi[5], mi[6], mi[7]));
+  }
 }
 
 struct BandGeom {
@@ -781,6 +787,12 @@ roi_pool_fwd_band_kernel(const float* __restrict__ bottom, const float* __restri
         unsigned q = col_a + (unsigned)hs * row_bytes;
         int cellC = LINEAR ? 0 : hs * WC + ws * C;
         int r = he - hs;
+        // Tried and dropped (B200, C4 workload, this loop = 3.49 ms): a flattened cell loop
+        // with the next cell's loads issued ahead, two register buffers at 768 threads (short
+        // scoreboard stalls 2.6 -> 1.5 per issue, but 2.87 G instead of 2.67 G instructions and
+        // 6 instead of 8 warps per scheduler: 3.62 ms); 16 channels per thread at 512 threads
+        // (4 warps per scheduler cannot hide the latency, 16 columns per warp diverge more:
+        // 5.47 ms).
 #pragma unroll 1
         do {
           const unsigned q_end = q + nw_bytes;
