@@ -299,15 +299,20 @@ def run_ours(args):
         value = world * B / (ms_step / 1e3)
         peak, peak_src = measured_peak()
         achieved = B * ROI_POOL_FWD_BYTES_PER_IMAGE / (roi_ms / 1e3) / 1e9
-        tiled = os.environ.get("WSSDL_ROI_FWD_KERNEL", "").startswith("t")
-        kname = "roi_pool_fwd_tiled_kernel" if tiled else "roi_pool_fwd_kernel"
+        # wssdl_roi_pool_fwd picks the band kernel for this workload (csrc/roi_pool.cu);
+        # WSSDL_ROI_FWD_KERNEL=direct|tiled forces the other two
+        kenv = os.environ.get("WSSDL_ROI_FWD_KERNEL", "")
+        kname, ktmpl, nlaunch = {
+            "d": ("roi_pool_fwd_kernel", "<4,CPU_TRUNC,128,2>", 2),
+            "t": ("roi_pool_fwd_tiled_kernel", "<CPU_TRUNC>", 3),
+        }.get(kenv[:1], ("roi_pool_fwd_band_kernel", "<CPU_TRUNC,argmax,linear>", 3))
         traffic, traffic_src = measured_traffic(kname, B)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": max(Wm, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(B, world),
-            "roofline": {"kernel": kname + ("<CPU_TRUNC>" if tiled else "<4,CPU_TRUNC,128,2>"),
+            "roofline": {"kernel": kname + ktmpl,
                          "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
@@ -315,9 +320,9 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": B * ROI_POOL_FWD_BYTES_PER_IMAGE,
                          "ms_per_launch": roi_ms},
             "kernels_ms_per_step": {"proposals_kernel": prop_ms, "roi_pool_fwd_kernel": roi_ms},
-            # proposals_kernel + roi_pool_fwd kernel (+ roi_bucket_kernel when the tiled
-            # kernel sorts RoIs by image) per step
-            "gpu_launches": (3 if tiled else 2) * K,
+            # proposals_kernel + roi_pool_fwd kernel (+ roi_bucket_kernel when a shared-memory
+            # kernel groups the RoIs by image; its few us are inside ms_per_launch) per step
+            "gpu_launches": nlaunch * K,
             "clocks": clocks,
             "rois_per_image": [int(counts.min()), int(counts.max())],
             "numa_node_rank0": numa,

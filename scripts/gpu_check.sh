@@ -27,8 +27,10 @@ if [ "${SKIP_NCU}" != "1" ]; then
   timeout 600 $NCU --metrics gpu__time_duration.sum -c 60 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
   FULL="$NCU --set full --import-source on -f"
-  timeout 600 $FULL -k regex:roi_pool_fwd_kernel -s 2 -c 1 -o gpurun_out/prof_roi_fwd \
+  timeout 600 $FULL -k regex:roi_pool_fwd_band -s 2 -c 1 -o gpurun_out/prof_roi_fwd_band \
       python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+  WSSDL_ROI_FWD_KERNEL=direct timeout 600 $FULL -k regex:roi_pool_fwd_kernel -s 2 -c 1 -o gpurun_out/prof_roi_fwd \
+      python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline >> gpurun_out/ncu_full.log 2>&1
   WSSDL_ROI_FWD_KERNEL=tiled timeout 600 $FULL -k regex:roi_pool_fwd_tiled -s 2 -c 1 -o gpurun_out/prof_roi_fwd_tiled \
       python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline >> gpurun_out/ncu_full.log 2>&1
   timeout 600 $FULL -k regex:proposals_kernel -s 2 -c 1 -o gpurun_out/prof_proposals \

@@ -550,33 +550,31 @@ constexpr int B_THREADS = 1024;
 constexpr int B_SCAN_MAX_R = 4096;
 constexpr int B_MAX_RB = 1024;
 
-// One bin whose rows are not all resident in this band: pooled straight from global memory.
-// Rare (RoIs several times taller than the map), so it is kept out of line.
+// One bin whose rows are not all resident in this band: pooled straight from global memory,
+// one channel at a time.  Rare (RoIs several times taller than the map, never the detector's
+// own proposals), so it is kept out of line and as small in registers as possible: the hot
+// loop's register allocation must not pay for it.  (A vectorised version that stored through
+// the st.v8 inline asm of st256 was narrowed to a scalar store by ptxas 12.9 in some clones of
+// the out-of-line function; caught by the tall-RoI test.)
 template <bool HAS_ARGMAX>
 __device__ __noinline__ void band_slow_bin(const float* __restrict__ img_base, int hs, int he,
                                            int ws, int nw, int W, int C, int c_lo,
                                            float* __restrict__ top_o, int* __restrict__ arg_o) {
-  float m[8];
-  int mi[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { m[k] = -FLT_MAX; mi[k] = -1; }
-  for (int h = hs; h < he; ++h)
-    for (int w = ws; w < ws + nw; ++w) {
-      const int cell = (h * W + w) * C + c_lo;
-      const float4 v0 = __ldg(reinterpret_cast<const float4*>(img_base + cell));
-      const float4 v1 = __ldg(reinterpret_cast<const float4*>(img_base + cell + 4));
-      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (v[k] > m[k]) { m[k] = v[k]; mi[k] = cell + k; }
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    float m = -FLT_MAX;
+    int mi = -1;
+#pragma unroll 1
+    for (int h = hs; h < he; ++h) {
+      int idx = (h * W + ws) * C + c_lo + k;
+#pragma unroll 1
+      for (int w = 0; w < nw; ++w, idx += C) {
+        const float v = __ldg(img_base + idx);
+        if (v > m) { m = v; mi = idx; }            // strict '>' (cc:187)
+      }
     }
-  // plain 128-bit stores: ptxas 12.9 narrows the st.v8 inline asm of st256 to a scalar store
-  // in some clones of this out-of-line function (seen in SASS; caught by the tall-RoI test)
-  __stcs(reinterpret_cast<float4*>(top_o), make_float4(m[0], m[1], m[2], m[3]));
-  __stcs(reinterpret_cast<float4*>(top_o) + 1, make_float4(m[4], m[5], m[6], m[7]));
-  if (HAS_ARGMAX) {
-    __stcs(reinterpret_cast<int4*>(arg_o), make_int4(mi[0], mi[1], mi[2], mi[3]));
-    __stcs(reinterpret_cast<int4*>(arg_o) + 1, make_int4(mi[4], mi[5], mi[6], mi[7]));
+    top_o[k] = m;
+    if (HAS_ARGMAX) arg_o[k] = mi;
   }
 }
 
@@ -1201,14 +1199,19 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
   // tiled while its grid fits one wave.
   const bool tiled_pays = tp.scan && (long long)(C / T_SLICE) * B * tp.nchunks <= WSSDL_NUM_SMS &&
                           PH * PW <= 64 && (long long)R * PH * PW * 2 >= (long long)B * H * W;
-  // The band kernel (128 B cells: conflict-free loads, full-line stores) takes the batched
-  // case: many RoIs per image re-reading a map that L2 would otherwise serve ~35x, bins
-  // small enough (7x7-like) that the direct kernel sits on the L2 cap.  WSSDL_ROI_FWD_KERNEL=band
-  // forces it.
+  // The band kernel (128 B cells: conflict-free loads, full-line stores) is the default
+  // wherever RoIs re-read the map and bins are small (7x7-like).  Measured on B200
+  // (profiles/r01_roi_fwd_direct_vs_tiled_vs_band.txt): C4 256 images 3.49 ms vs 3.58 direct /
+  // 3.59 tiled; C1 31.6 us vs 37 / 35; C2 24.5 us vs 34 / 29.  It loses where its grid is a
+  // few ragged waves (16 images: 512 CTAs = 3.5 waves, 0.261 vs 0.250 ms direct) and on big
+  // bins (C3 14x14x1024: the direct kernel already runs at the HBM roofline), so: one wave
+  // or at least 8.  WSSDL_ROI_FWD_KERNEL=band forces it.
   const int band_env = (kenv && kenv[0] == 'b') ? 1 : 0;
   const BandPlan bp = plan_band(B, H, W, C, R, PH, PW, vec4 && al32, workspace_bytes);
-  const bool band_pays = kernel_env == 0 && !tiled_pays && PH * PW <= 64 &&
-                         (long long)R * PH * PW >= 4ll * B * H * W && bp.g.NB <= 4;
+  const long long band_ctas = (long long)(C / B_SLICE) * (B > 0 ? B : 1) * bp.g.NB * bp.nchunks;
+  const bool band_pays = kernel_env == 0 && PH * PW <= 64 &&
+                         (long long)R * PH * PW * 2 >= (long long)B * H * W && bp.g.NB <= 4 &&
+                         (band_ctas <= WSSDL_NUM_SMS || band_ctas >= 8ll * WSSDL_NUM_SMS);
   if (bp.ok && (band_env || band_pays)) {
     int* img_start = nullptr;
     int* perm = nullptr;
