@@ -15,6 +15,15 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
+@pytest.fixture(autouse=True, params=["cta", "cluster"])
+def proposals_variant(request, monkeypatch):
+    """Every test runs twice: one CTA per image, and a thread-block cluster of 8 CTAs per
+    image (csrc/proposal.cu: the keep-list NMS is split over the cluster and its partial
+    bitmaps are exchanged through distributed shared memory).  The default picks by batch size."""
+    monkeypatch.setenv("WSSDL_PROPOSALS_CLUSTER", "1" if request.param == "cluster" else "0")
+    return request.param
+
+
 def _run(oracle_mod, seed, B, H, W, pre, post, thresh=0.7, im_h=600, im_w=800, scale=1.0,
          sigma=None):
     cls, reg, info = syn.rpn_outputs(seed, B, H, W, 9, im_h=im_h, im_w=im_w, im_scale=scale)
