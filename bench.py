@@ -304,8 +304,8 @@ def run_ours(args):
         kenv = os.environ.get("WSSDL_ROI_FWD_KERNEL", "")
         kname, ktmpl, nlaunch = {
             "d": ("roi_pool_fwd_kernel", "<4,CPU_TRUNC,128,2>", 2),
-            "t": ("roi_pool_fwd_tiled_kernel", "<CPU_TRUNC>", 3),
-        }.get(kenv[:1], ("roi_pool_fwd_band_kernel", "<CPU_TRUNC,argmax,linear>", 3))
+            "t": ("roi_pool_fwd_tiled_kernel", "<CPU_TRUNC>", 4),
+        }.get(kenv[:1], ("roi_pool_fwd_band_kernel", "<CPU_TRUNC,argmax,linear>", 4))
         traffic, traffic_src = measured_traffic(kname, B)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
@@ -320,8 +320,9 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": B * ROI_POOL_FWD_BYTES_PER_IMAGE,
                          "ms_per_launch": roi_ms},
             "kernels_ms_per_step": {"proposals_kernel": prop_ms, "roi_pool_fwd_kernel": roi_ms},
-            # proposals_kernel + roi_pool_fwd kernel (+ roi_bucket_kernel when a shared-memory
-            # kernel groups the RoIs by image; its few us are inside ms_per_launch) per step
+            # proposals_kernel + roi_pool_fwd kernel (+ roi_hist_kernel and roi_scatter_kernel
+            # when a shared-memory kernel groups the RoIs by image; their few us are inside
+            # ms_per_launch) per step
             "gpu_launches": nlaunch * K,
             "clocks": clocks,
             "rois_per_image": [int(counts.min()), int(counts.max())],

@@ -9,6 +9,14 @@ from wssdl_bus_b200 import ops, synthetic as syn
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["cta", "cluster"])
+def sweep_variant(request, monkeypatch):
+    """Every test runs twice: the single-CTA sweep and the sweep over a thread-block cluster
+    of 8 CTAs (csrc/nms.cu; the default picks the cluster from N = 32768)."""
+    monkeypatch.setenv("WSSDL_NMS_SWEEP_CLUSTER", "1" if request.param == "cluster" else "0")
+    return request.param
+
+
 def _oracle_nms(oracle_mod, d, t, variant=0):
     if variant == 0 and oracle_mod.ref.available() and d.shape[0] <= 3000:
         return oracle_mod.ref.cpu_nms(d, t)
