@@ -176,7 +176,7 @@ roi_pool_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
 //     cp.async.bulk shared->global copies (64 B per bin column and tensor) to take the stores
 //     off the LSU data pipe -- bit-exact but 6.3 ms instead of 3.6 ms on the C4 workload: 64 B
 //     transfers are TMA-issue bound (about one per 3.7 cycles per SM) and the warps spin in
-//     wait_group.read (profiles/r01_roi_fwd_direct_vs_tiled.txt);
+//     wait_group.read (profiles/history/r01_roi_fwd_direct_vs_tiled.txt);
 //   - RoIs are grouped by image either by an in-CTA scan of the batch column (R <=
 //     T_SCAN_MAX_R, no workspace) or by a counting-sort pre-pass (launch_roi_bucket) into
 //     the caller's workspace.  Bucket B collects RoIs whose batch index is outside [0,B):
@@ -1234,7 +1234,7 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
   // the tiled kernel stores 256 bits per lane: outputs must be 32-byte aligned
   const bool al32 = ((reinterpret_cast<uintptr_t>(top) | reinterpret_cast<uintptr_t>(argmax)) & 31u) == 0;
   const TiledPlan tp = plan_tiled(B, H, W, C, R, PH, PW, vec4 && al32, workspace_bytes);
-  // Measured on B200 (profiles/r01_roi_fwd_direct_vs_tiled.txt): the tiled kernel wins for
+  // Measured on B200 (profiles/history/r01_roi_fwd_direct_vs_tiled.txt): the tiled kernel wins for
   // one or two images (C1/C2: the direct kernel cannot fill the machine with latency-bound
   // L2 reads), ties at 256 images (3.63 vs 3.57 ms: LSU wavefronts / issue slots vs the L2
   // throughput cap) and loses when bins are large (C3, 14x14 on 1024 channels).  Default:
