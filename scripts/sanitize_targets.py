@@ -15,23 +15,35 @@ from wssdl_bus_b200.rpn_msr.generate_anchors import generate_anchors  # noqa: E4
 B, H, W, C = 2, 38, 50, 32
 feat = torch.from_numpy(syn.feature_map(0, B, H, W, C)).cuda()
 rois = np.concatenate([syn.rois_for_pool(1, 90, B), syn.adversarial_rois(B, W, H)])
-for kern in ("direct", "tiled"):
+for kern in ("direct", "tiled", "band"):
     os.environ["WSSDL_ROI_FWD_KERNEL"] = kern
     for mode in ("cpu", "gpu"):
         top, arg = ops.roi_pool_forward(feat, rois, 7, 7, 1 / 16., bin_mode=mode)
-# counting-sort pre-pass (R > 4096)
+# band kernel, linear-index variant (C % 128 == 0) incl. bins taller than the band overlap
+feat128 = torch.from_numpy(syn.feature_map(9, B, H, W, 128)).cuda()
+tall = np.array([[0, 100, -900, 500, 1700], [1, 0, 0, 799, 599]], np.float32)
+ops.roi_pool_forward(feat128, np.concatenate([rois, tall]), 7, 7, 1 / 16.)
+# counting-sort pre-pass (R > 4096): histogram + scatter kernels, then tiled / band
 big = syn.rois_for_pool(2, 4200, B)
-top2, arg2 = ops.roi_pool_forward(feat, big, 7, 7, 1 / 16.)
+for kern in ("tiled", "band"):
+    os.environ["WSSDL_ROI_FWD_KERNEL"] = kern
+    top2, arg2 = ops.roi_pool_forward(feat, big, 7, 7, 1 / 16.)
 os.environ.pop("WSSDL_ROI_FWD_KERNEL")
 g = torch.randn_like(top)
 for det in (False, True):
     ops.roi_pool_backward((B, H, W, C), rois, arg, g, 7, 7, 1 / 16., deterministic=det)
 cls, reg, info = syn.rpn_outputs(3, B, H, W, 9)
-ops.proposals(cls, reg, info, generate_anchors(), 16, 6000, 300, 0.7, 16)
-ops.proposals(cls, reg, info, generate_anchors(), 16, 2000, 500, 0.7, 16, want_decoded=True)
+for cl in ("0", "1"):     # one CTA per image / cluster of 8 CTAs per image
+    os.environ["WSSDL_PROPOSALS_CLUSTER"] = cl
+    ops.proposals(cls, reg, info, generate_anchors(), 16, 6000, 300, 0.7, 16)
+    ops.proposals(cls, reg, info, generate_anchors(), 16, 2000, 500, 0.7, 16, want_decoded=True)
+os.environ.pop("WSSDL_PROPOSALS_CLUSTER")
 d = syn.dets(4, 5000)
-ops.nms(d, 0.7)
-ops.nms(d, 0.3, mode=ops.NMS_GT_F32 | ops.NMS_CONTAIN)
+for cl in ("0", "1"):     # single-CTA sweep / cluster sweep
+    os.environ["WSSDL_NMS_SWEEP_CLUSTER"] = cl
+    ops.nms(d, 0.7)
+    ops.nms(d, 0.3, mode=ops.NMS_GT_F32 | ops.NMS_CONTAIN)
+os.environ.pop("WSSDL_NMS_SWEEP_CLUSTER")
 b = syn.random_boxes(5, 3000).astype(np.float64)
 q = syn.random_boxes(6, 130).astype(np.float64)
 ops.bbox_overlaps(b, q)

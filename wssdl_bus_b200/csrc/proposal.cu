@@ -192,7 +192,13 @@ proposals_kernel(const PropParams p) {
   __shared__ unsigned s_sup[XCHG_WORDS];            // this CTA's partial "suppressed" bitmap
   namespace cg = cooperative_groups;
   int crank = 0;
-  if constexpr (CS > 1) crank = (int)cg::this_cluster().block_rank();
+  if constexpr (CS > 1) {
+    crank = (int)cg::this_cluster().block_rank();
+    // distributed shared memory may only be touched once every CTA of the cluster has started
+    // (compute-sanitizer: "block that might not have entered yet"); the first remote store is
+    // far away, but the guarantee has to be explicit
+    cg::this_cluster().sync();
+  }
   const bool writer = crank == 0;
   // layout: sort buffer (kpad u64) | histogram/scalars | UNION { keys (NA u32), live in phases
   // 1-3 ; per-chunk NMS state + kept list, live in phase 4 }.  The score keys are dead once
