@@ -40,6 +40,12 @@ def _worker(rank, world, port, n_images, post, ret):
     d2, c2 = unshard_detections(boxes, counts, n_images)
     s2, _ = unshard_detections(scores, counts, n_images)
     ok = ok and torch.equal(d2, d) and torch.equal(c2, c) and torch.equal(s2, d[:, :, 4])
+    # asynchronous form (the bench overlaps the gather with the RoI pooling): same tensors
+    (b3, s3, c3), works = all_gather_blobs([det, det[:, :, 4].contiguous(), cnt], async_op=True)
+    ok = ok and len(works) == 3
+    for w in works:
+        w.wait()
+    ok = ok and torch.equal(b3, boxes) and torch.equal(s3, scores) and torch.equal(c3, counts)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

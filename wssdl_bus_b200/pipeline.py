@@ -81,20 +81,28 @@ class HotPath:
         return p["rois"].view(B, self.post, 5), p["scores"].view(B, self.post), p["counts"]
 
 
-def all_gather_blobs(tensors, group=None):
+def all_gather_blobs(tensors, group=None, async_op=False):
     """all_gather_into_tensor of several [n_local, ...] tensors (NCCL over NVLink on GPUs,
-    gloo in the CPU tests): -> list of [world, n_local, ...]."""
+    gloo in the CPU tests): -> list of [world, n_local, ...].
+
+    async_op=True returns (list, works): the collectives are enqueued behind the work already
+    on the current stream and run on the communicator's own stream, so kernels launched
+    afterwards on the current stream overlap them (the detections depend on the proposals
+    only, so a step gathers them WHILE its RoI pooling runs); call wait() on every work before
+    the gathered tensors are read."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    out = []
+    out, works = [], []
     for t in tensors:
         if world == 1:
             out.append(t[None])
             continue
         g = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(g, t.contiguous(), group=group)
+        w = dist.all_gather_into_tensor(g, t.contiguous(), group=group, async_op=async_op)
+        if async_op:
+            works.append(w)
         out.append(g.reshape((world, t.shape[0]) + tuple(t.shape[1:])))
-    return out
+    return (out, works) if async_op else out
 
 
 def all_gather_detections(det, counts, group=None):
