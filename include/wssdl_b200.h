@@ -58,9 +58,14 @@ const char* wssdl_error_string(int code);   /* static string, also for cudaError
  * anything else runs the scalar variant of the direct kernel.
  * workspace   optional scratch of wssdl_roi_pool_fwd_workspace_bytes(B, R) bytes (device,
  *             4-byte aligned; may be NULL).  With it, batches of more than 4096 RoIs can
- *             use the shared-memory-resident kernel (RoIs are counting-sorted by image into
- *             the workspace first); without it they run the direct kernel.  Results are
- *             identical either way.
+ *             use the shared-memory-resident kernels (RoIs are counting-sorted by image into
+ *             the workspace first, two small kernels on the same stream); without it they
+ *             run the direct kernel.  Results are identical either way.
+ * Three kernels give the same bytes and are picked by shape (csrc/roi_pool.cu): "band"
+ * (32-channel slice of overlapping row bands of the map in shared memory; the detector's
+ * 7x7 shapes), "direct" (one CTA per output row reading L2; big bins, awkward grid sizes),
+ * "tiled" (16-channel slice of the whole map; C % 32 != 0).  The environment variable
+ * WSSDL_ROI_FWD_KERNEL=band|direct|tiled forces one where the shape allows (experiments).
  */
 enum { WSSDL_BIN_CPU_TRUNC = 0, WSSDL_BIN_GPU_CEIL = 1 };
 
@@ -158,7 +163,10 @@ int wssdl_bbox_transform(const float* ex_rois, const float* gt_rois, int N, floa
  * Replaces proposal_layer (rpn_msr/proposal_layer_tf_bus.py:19-148): anchors generated on
  * the fly (generate_anchors.py:37-97 + shifts :55-71), bbox_transform_inv, clip_boxes,
  * _filter_boxes (:151-156), score sort + pre-NMS top-N (:129-133), NMS (:138), post-NMS
- * top-N (:139-146), batched over images: one CTA per image, everything in shared memory.
+ * top-N (:139-146), batched over images: one CTA per image, everything in shared memory
+ * (small batches: a thread-block cluster of 8 CTAs per image splits the keep-list NMS and
+ * exchanges its partial bitmaps through distributed shared memory; same results;
+ * WSSDL_PROPOSALS_CLUSTER=0|1 overrides the choice).
  *
  * cls_prob  [B,H,W,2A] f32 NHWC (fg score of anchor a = channel A+a, :86)
  * bbox_pred [B,H,W,4A] f32 NHWC (deltas of anchor a = channels 4a..4a+3, :106)
