@@ -71,6 +71,15 @@ enum { WSSDL_BIN_CPU_TRUNC = 0, WSSDL_BIN_GPU_CEIL = 1 };
 
 size_t wssdl_roi_pool_fwd_workspace_bytes(int B, int R);
 
+/* Host-only query (no CUDA call): which forward kernel a call of this shape takes and its
+ * launch geometry, for tests and tuning.  force: 0 = by shape, 1 = direct, 2 = tiled,
+ * 3 = band.  out[8] = { kernel (0 direct, 1 tiled, 2 band), row bands per image, rows per
+ * band, first-row distance of two bands, RoI chunks per image, RoIs whose bin edges are
+ * resident at a time, dynamic shared memory bytes, 1 if the RoI lists are built in-kernel }.
+ * Assumes aligned pointers. */
+int wssdl_roi_pool_fwd_plan(int B, int H, int W, int C, int R, int PH, int PW,
+                            int with_workspace, int force, int* out);
+
 int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B, int H, int W, int C,
                        int R, int PH, int PW, float spatial_scale, int bin_mode,
                        float* top, int* argmax, void* workspace, size_t workspace_bytes,

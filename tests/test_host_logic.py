@@ -54,3 +54,70 @@ def test_numa_binding_is_a_noop_without_a_visible_topology():
     before = os.sched_getaffinity(0)
     assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), int)
     assert os.sched_getaffinity(0) <= before and len(os.sched_getaffinity(0)) > 0
+
+
+# ---------------------------------------------------------------- RoI-pool forward dispatch
+# wssdl_roi_pool_fwd_plan is a host-only query (no CUDA call): the kernel a shape takes and the
+# row-band geometry of the band kernel (csrc/roi_pool.cu: choose_fwd / plan_band).
+DIRECT, TILED, BAND = 0, 1, 2
+
+
+def _plan(B, H, W, C, R, PH, PW, ws=True, force=0):
+    import ctypes
+    from wssdl_bus_b200 import _lib
+    out = (ctypes.c_int * 8)()
+    rc = _lib.lib().wssdl_roi_pool_fwd_plan(B, H, W, C, R, PH, PW, int(ws), force, out)
+    assert rc == 0
+    return dict(zip(("kernel", "NB", "Hb", "step", "nchunks", "RB", "smem", "scan"), list(out)))
+
+
+def test_fwd_kernel_choice_on_the_baseline_shapes():
+    # C4 (the bench workload): band kernel, two bands of 23 rows, RoI lists from the workspace
+    p = _plan(256, 38, 50, 512, 256 * 300, 7, 7)
+    assert (p["kernel"], p["NB"], p["Hb"], p["step"], p["scan"]) == (BAND, 2, 23, 15, 0)
+    # C1 / C2 (one image): band kernel, lists built in-kernel, RoIs split so the grid is one wave
+    for R in (300, 128):
+        p = _plan(1, 38, 50, 512, R, 7, 7)
+        assert p["kernel"] == BAND and p["scan"] == 1
+        assert (512 // 32) * p["NB"] * p["nchunks"] <= 148
+    # C3 (14x14 bins on 1024 channels) and a grid of a few ragged waves: direct kernel
+    assert _plan(16, 38, 50, 1024, 4800, 14, 14)["kernel"] == DIRECT
+    assert _plan(16, 38, 50, 512, 16 * 300, 7, 7)["kernel"] == DIRECT
+    # C % 32 != 0: the 16-channel tiled kernel takes single images; C % 16 != 0: direct
+    assert _plan(1, 38, 50, 48, 300, 7, 7)["kernel"] == TILED
+    assert _plan(1, 38, 50, 20, 300, 7, 7)["kernel"] == DIRECT
+    # > 4096 RoIs without a workspace: nothing to group them with
+    assert _plan(256, 38, 50, 512, 256 * 300, 7, 7, ws=False)["kernel"] == DIRECT
+    # forcing
+    assert _plan(256, 38, 50, 512, 256 * 300, 7, 7, force=1)["kernel"] == DIRECT
+    assert _plan(256, 38, 50, 512, 256 * 300, 7, 7, force=2)["kernel"] == TILED
+    assert _plan(16, 38, 50, 1024, 4800, 14, 14, force=3)["kernel"] == BAND
+
+
+def test_band_geometry_invariants():
+    """Seeded sweep of shapes: whenever the band kernel is available its bands cover the map,
+    overlap by at least the tallest bin of a RoI inside the map (+1 for GPU_CEIL edges), and
+    the CTA's shared memory (map + bin-edge tables + lists) fits the 227 KB carve-out."""
+    rng = np.random.default_rng(7)
+    seen_multi = 0
+    for _ in range(400):
+        B = int(rng.integers(1, 40))
+        H, W = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+        C = int(rng.choice([32, 64, 128, 256, 512, 1024]))
+        R = int(rng.choice([1, 17, 300, 4096, 4097, 20000]))
+        PH, PW = int(rng.integers(1, 15)), int(rng.integers(1, 15))
+        p = _plan(B, H, W, C, R, PH, PW, force=3)
+        if p["kernel"] != BAND:
+            continue
+        NB, Hb, step = p["NB"], p["Hb"], p["step"]
+        assert NB >= 1 and step >= 1 and 1 <= Hb <= H
+        assert (NB - 1) * step + Hb >= H                      # the last band reaches the last row
+        if NB > 1:
+            seen_multi += 1
+            ov = Hb - step
+            assert ov >= -(-(H + 1) // PH) + 2                # ceil((H+1)/PH) + 2
+            assert (NB - 2) * step + Hb < H + step            # no band is superfluous
+        assert Hb * W * 128 + 128 <= p["smem"] <= 227 * 1024 - 1024
+        assert p["RB"] >= min(R, 16) and p["nchunks"] >= 1
+        assert p["scan"] == (1 if R <= 4096 else 0)
+    assert seen_multi > 20

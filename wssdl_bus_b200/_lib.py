@@ -25,6 +25,7 @@ SIGNATURES = {
     "wssdl_version": (_i, []),
     "wssdl_error_string": (ctypes.c_char_p, [_i]),
     "wssdl_roi_pool_fwd_workspace_bytes": (_sz, [_i, _i]),
+    "wssdl_roi_pool_fwd_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "wssdl_roi_pool_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _sz,
                                 _vp]),
     "wssdl_roi_pool_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),

@@ -1202,6 +1202,68 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+namespace {
+
+// Which forward kernel a call takes, and its launch geometry.  One function for the launcher
+// and for the host-only query wssdl_roi_pool_fwd_plan (CPU tests check the invariants).
+enum { FWD_DIRECT = 0, FWD_TILED = 1, FWD_BAND = 2 };
+struct FwdChoice {
+  int kernel;
+  TiledPlan tp;
+  BandPlan bp;
+};
+
+// force: 0 = by shape, 1 = direct, 2 = tiled, 3 = band (WSSDL_ROI_FWD_KERNEL).  aligned = the
+// pointer requirements of the shared-memory kernels hold (16 B inputs, 32 B outputs, C % 4).
+FwdChoice choose_fwd(int B, int H, int W, int C, int R, int PH, int PW, bool aligned,
+                     size_t workspace_bytes, int force) {
+  FwdChoice c;
+  c.kernel = FWD_DIRECT;
+  c.tp = plan_tiled(B, H, W, C, R, PH, PW, aligned, workspace_bytes);
+  c.bp = plan_band(B, H, W, C, R, PH, PW, aligned, workspace_bytes);
+  const bool reuse = PH * PW <= 64 && (long long)R * PH * PW * 2 >= (long long)B * H * W;
+  // The tiled kernel (profiles/history/r01_roi_fwd_direct_vs_tiled.txt) wins over the direct
+  // one for one or two images, ties at 256 images and loses when bins are large: tiled while
+  // its grid fits one wave.  Since the band kernel it only takes what that one cannot
+  // (C % 32 != 0).
+  const bool tiled_pays = c.tp.scan && reuse &&
+                          (long long)(C / T_SLICE) * B * c.tp.nchunks <= WSSDL_NUM_SMS;
+  // The band kernel (128 B cells: conflict-free loads, full-line stores) is the default
+  // wherever RoIs re-read the map and bins are small (7x7-like).  Measured on B200
+  // (profiles/r01_roi_fwd_direct_vs_tiled_vs_band.txt): C4 256 images 3.45 ms vs 3.64 direct /
+  // 3.54 tiled; C1 31.7 us vs 38 / 35; C2 24.6 us vs 36 / 29.  It loses where its grid is a
+  // few ragged waves (16 images: 512 CTAs = 3.5 waves, 0.268 vs 0.250 ms direct) and on big
+  // bins (C3 14x14x1024: the direct kernel already runs at the HBM roofline), so: one wave
+  // or at least 8.
+  const long long band_ctas =
+      (long long)(C / B_SLICE) * (B > 0 ? B : 1) * c.bp.g.NB * c.bp.nchunks;
+  const bool band_pays = reuse && c.bp.g.NB <= 4 &&
+                         (band_ctas <= WSSDL_NUM_SMS || band_ctas >= 8ll * WSSDL_NUM_SMS);
+  if (c.bp.ok && (force == 3 || (force == 0 && band_pays))) c.kernel = FWD_BAND;
+  else if (c.tp.ok && force != 1 && (force == 2 || tiled_pays)) c.kernel = FWD_TILED;
+  return c;
+}
+
+}  // namespace
+
+extern "C" int wssdl_roi_pool_fwd_plan(int B, int H, int W, int C, int R, int PH, int PW,
+                                       int with_workspace, int force, int* out) {
+  if (!out || B < 0 || H < 0 || W < 0 || C < 0 || R < 0 || PH < 0 || PW < 0) return WSSDL_EINVAL;
+  if (force < 0 || force > 3) return WSSDL_EINVAL;
+  const size_t ws = with_workspace ? tiled_workspace_bytes(B, R) : 0;
+  const FwdChoice c = choose_fwd(B, H, W, C, R, PH, PW, C % 4 == 0, ws, force);
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  out[0] = c.kernel;
+  if (c.kernel == FWD_BAND) {
+    out[1] = c.bp.g.NB; out[2] = c.bp.g.Hb; out[3] = c.bp.g.step; out[4] = c.bp.nchunks;
+    out[5] = c.bp.RB; out[6] = (int)c.bp.smem; out[7] = c.bp.scan ? 1 : 0;
+  } else if (c.kernel == FWD_TILED) {
+    out[1] = 1; out[2] = H; out[3] = H; out[4] = c.tp.nchunks;
+    out[5] = c.tp.RB; out[6] = (int)c.tp.smem; out[7] = c.tp.scan ? 1 : 0;
+  }
+  return WSSDL_OK;
+}
+
 extern "C" size_t wssdl_roi_pool_fwd_workspace_bytes(int B, int R) {
   if (B < 0 || R < 0) return 0;
   return tiled_workspace_bytes(B, R);
@@ -1222,39 +1284,18 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
                     (argmax == nullptr || aligned16(argmax));
   cudaStream_t s = to_cuda(stream);
 
-  // Kernel choice.  The tiled kernel wins whenever RoIs of an image overlap enough for the
-  // map to be re-read several times (the detector's case: hundreds of RoIs per image on a
-  // map of a few thousand cells); experiments: WSSDL_ROI_FWD_KERNEL=direct|tiled,
-  // WSSDL_ROI_FWD_STREAM_ST=0|1.
-  // (read per call so tests can force either kernel)
+  // Kernel choice (choose_fwd above).  Experiments: WSSDL_ROI_FWD_KERNEL=direct|tiled|band
+  // (read per call so tests can force a kernel), WSSDL_ROI_FWD_STREAM_ST=0|1.
   const char* kenv = getenv("WSSDL_ROI_FWD_KERNEL");
-  const int kernel_env = !kenv ? 0 : (kenv[0] == 'd' ? 1 : (kenv[0] == 't' ? 2 : 0));
+  const int force = !kenv ? 0 : (kenv[0] == 'd' ? 1 : (kenv[0] == 't' ? 2 : (kenv[0] == 'b' ? 3 : 0)));
   const int stream_st = env_int("WSSDL_ROI_FWD_STREAM_ST", 1);
   if (workspace == nullptr) workspace_bytes = 0;
-  // the tiled kernel stores 256 bits per lane: outputs must be 32-byte aligned
+  // the shared-memory kernels store 256 bits per lane: outputs must be 32-byte aligned
   const bool al32 = ((reinterpret_cast<uintptr_t>(top) | reinterpret_cast<uintptr_t>(argmax)) & 31u) == 0;
-  const TiledPlan tp = plan_tiled(B, H, W, C, R, PH, PW, vec4 && al32, workspace_bytes);
-  // Measured on B200 (profiles/history/r01_roi_fwd_direct_vs_tiled.txt): the tiled kernel wins for
-  // one or two images (C1/C2: the direct kernel cannot fill the machine with latency-bound
-  // L2 reads), ties at 256 images (3.63 vs 3.57 ms: LSU wavefronts / issue slots vs the L2
-  // throughput cap) and loses when bins are large (C3, 14x14 on 1024 channels).  Default:
-  // tiled while its grid fits one wave.
-  const bool tiled_pays = tp.scan && (long long)(C / T_SLICE) * B * tp.nchunks <= WSSDL_NUM_SMS &&
-                          PH * PW <= 64 && (long long)R * PH * PW * 2 >= (long long)B * H * W;
-  // The band kernel (128 B cells: conflict-free loads, full-line stores) is the default
-  // wherever RoIs re-read the map and bins are small (7x7-like).  Measured on B200
-  // (profiles/r01_roi_fwd_direct_vs_tiled_vs_band.txt): C4 256 images 3.49 ms vs 3.58 direct /
-  // 3.59 tiled; C1 31.6 us vs 37 / 35; C2 24.5 us vs 34 / 29.  It loses where its grid is a
-  // few ragged waves (16 images: 512 CTAs = 3.5 waves, 0.261 vs 0.250 ms direct) and on big
-  // bins (C3 14x14x1024: the direct kernel already runs at the HBM roofline), so: one wave
-  // or at least 8.  WSSDL_ROI_FWD_KERNEL=band forces it.
-  const int band_env = (kenv && kenv[0] == 'b') ? 1 : 0;
-  const BandPlan bp = plan_band(B, H, W, C, R, PH, PW, vec4 && al32, workspace_bytes);
-  const long long band_ctas = (long long)(C / B_SLICE) * (B > 0 ? B : 1) * bp.g.NB * bp.nchunks;
-  const bool band_pays = kernel_env == 0 && PH * PW <= 64 &&
-                         (long long)R * PH * PW * 2 >= (long long)B * H * W && bp.g.NB <= 4 &&
-                         (band_ctas <= WSSDL_NUM_SMS || band_ctas >= 8ll * WSSDL_NUM_SMS);
-  if (bp.ok && (band_env || band_pays)) {
+  const FwdChoice choice = choose_fwd(B, H, W, C, R, PH, PW, vec4 && al32, workspace_bytes, force);
+  const TiledPlan& tp = choice.tp;
+  const BandPlan& bp = choice.bp;
+  if (choice.kernel == FWD_BAND) {
     int* img_start = nullptr;
     int* perm = nullptr;
     if (!bp.scan) {
@@ -1291,7 +1332,7 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
     WSSDL_CHECK_LAUNCH();
     return WSSDL_OK;
   }
-  if (tp.ok && kernel_env != 1 && (tiled_pays || kernel_env == 2)) {
+  if (choice.kernel == FWD_TILED) {
     int* img_start = nullptr;
     int* perm = nullptr;
     if (!tp.scan) {
