@@ -150,41 +150,64 @@ nms_mask_kernel(const float4* __restrict__ boxes, const float* __restrict__ area
 }
 
 constexpr int SWEEP_THREADS = 1024;
+constexpr int SWEEP_OR_THREADS = SWEEP_THREADS - 32;   // warps 1..31 run the OR phase
 
 // Single-CTA sweep.  remv (one bit per sorted box) lives in shared memory.
+//
+// Per 64-row block b: warp 0 RESOLVES the block (fixed point of "alive and not suppressed by
+// a kept earlier row of the block" on the diagonal word), then the kept rows are ORed into the
+// removal bitmap of the later column blocks.  Those two steps used to run back to back, the
+// second one an L2-latency-bound gather on the critical path of every block.  They are now
+// software pipelined over the warps: while warp 0 resolves block b, warps 1..31 OR the kept
+// rows of block b-1 into columns >= b+1.  Warp 0 needs column b of block b-1 before that OR
+// phase has run, so it fetches the 64 words mask[rows of block b-1][b] itself one block ahead
+// (they do not depend on what is kept) and reduces the kept ones with two warp ORs
+// (`fast`).  One barrier per block; the critical path per block is max(resolve, OR phase)
+// instead of their sum.
 __global__ void __launch_bounds__(SWEEP_THREADS)
 nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blocks,
                  const int* __restrict__ order, int max_keep, int* __restrict__ keep,
                  int* __restrict__ num_keep) {
   extern __shared__ unsigned long long remv[];   // col_blocks words
-  __shared__ unsigned long long s_kept;
+  __shared__ unsigned long long s_kept[2];       // kept mask of block b at [b & 1]
   __shared__ int s_count;
-  __shared__ int s_rows[64];                     // kept rows of the current block
+  __shared__ int s_rows[2][64];                  // kept rows of block b at [b & 1]
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < col_blocks; i += SWEEP_THREADS) remv[i] = 0;
-  if (tid == 0) s_count = 0;
+  if (tid == 0) { s_count = 0; s_kept[0] = 0ull; s_kept[1] = 0ull; }
   __syncthreads();
   const int limit = max_keep > 0 ? min(max_keep, N) : N;
 
-  // diagonal words of rows 64b+lane and 64b+32+lane (warp 0), fetched one block ahead: they
-  // do not depend on the removal bitmap, only their interpretation does
-  unsigned long long nd0 = 0ull, nd1 = 0ull;
+  // warp 0, fetched one block ahead: the diagonal words of rows 64b+lane and 64b+32+lane
+  // (nd*) and the words of the same rows in column b+1 (nc*); neither depends on the
+  // removal bitmap, only their interpretation does
+  unsigned long long nd0 = 0ull, nd1 = 0ull, nc0 = 0ull, nc1 = 0ull;
   if (tid < 32) {
     nd0 = lane < N ? mask[(size_t)lane * col_blocks] : 0ull;
     nd1 = lane + 32 < N ? mask[(size_t)(lane + 32) * col_blocks] : 0ull;
+    if (col_blocks > 1) {
+      nc0 = lane < N ? mask[(size_t)lane * col_blocks + 1] : 0ull;
+      nc1 = lane + 32 < N ? mask[(size_t)(lane + 32) * col_blocks + 1] : 0ull;
+    }
   }
+  unsigned long long fast = 0ull;                // block b-1's removals in column b (warp 0)
   for (int b = 0; b < col_blocks; ++b) {
     if (tid < 32) {
+      // ---- resolve block b
       const int r0 = 64 * b + lane, r1 = r0 + 32;
-      const unsigned long long d0 = nd0, d1 = nd1;
+      const unsigned long long d0 = nd0, d1 = nd1, c0 = nc0, c1 = nc1;
       if (b + 1 < col_blocks) {
         const int q0 = r0 + 64, q1 = r1 + 64;
         nd0 = q0 < N ? mask[(size_t)q0 * col_blocks + b + 1] : 0ull;
         nd1 = q1 < N ? mask[(size_t)q1 * col_blocks + b + 1] : 0ull;
+        if (b + 2 < col_blocks) {
+          nc0 = q0 < N ? mask[(size_t)q0 * col_blocks + b + 2] : 0ull;
+          nc1 = q1 < N ? mask[(size_t)q1 * col_blocks + b + 2] : 0ull;
+        }
       }
       const int nrow = min(64, N - 64 * b);
       const unsigned long long valid = nrow == 64 ? ~0ull : ((1ull << nrow) - 1ull);
-      const unsigned long long alive = ~remv[b] & valid;
+      const unsigned long long alive = ~(remv[b] | fast) & valid;
       unsigned long long K = alive;
       for (int it = 0; it < 64; ++it) {
         unsigned long long mine = 0;
@@ -204,58 +227,70 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blo
         while (over-- > 0) K &= ~(1ull << (63 - __clzll(K)));
         take = limit - count;
       }
+      // what the kept rows of this block remove in column b+1 (for the next resolve)
+      {
+        unsigned long long mine = 0;
+        if ((K >> lane) & 1ull) mine |= c0;
+        if ((K >> (lane + 32)) & 1ull) mine |= c1;
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)mine);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(mine >> 32));
+        fast = ((unsigned long long)hi << 32) | lo;
+      }
       // write kept indices in order
       if ((K >> lane) & 1ull)
         keep[count + __popcll(K & ((1ull << lane) - 1ull))] = order[r0];
       if ((K >> (lane + 32)) & 1ull)
         keep[count + __popcll(K & ((1ull << (lane + 32)) - 1ull))] = order[r1];
+      // the OR phase of this block runs in the NEXT iteration (warps 1..31)
+      if ((K >> lane) & 1ull) s_rows[b & 1][__popcll(K & ((1ull << lane) - 1ull))] = lane;
+      if ((K >> (lane + 32)) & 1ull)
+        s_rows[b & 1][__popcll(K & ((1ull << (lane + 32)) - 1ull))] = lane + 32;
       __syncwarp();                       // every lane has read s_count (racecheck: WAR)
-      if (lane == 0) { s_kept = K; s_count = count + take; }
-    }
-    __syncthreads();
-    const unsigned long long K = s_kept;
-    if (s_count >= limit) break;
-    // OR the kept rows of this block into the removal bitmap of the later column blocks.
-    // (kept row, column) pairs are spread over the whole CTA -- RP row parts x columns --
-    // and every thread issues its loads four at a time before using them: one thread per
-    // column walking its <= 64 rows serialised 64 L2 latencies per block (17 us/block).
-    const int nc = col_blocks - (b + 1);
-    if (nc > 0 && K != 0ull) {
-      if (tid < 64) {
-        if ((K >> tid) & 1ull) s_rows[__popcll(K & ((1ull << tid) - 1ull))] = tid;
-      }
-      __syncthreads();
-      const int kc = __popcll(K);
-      int rp_log2 = 0;
-      while (rp_log2 < 5 && ((nc << (rp_log2 + 1)) <= SWEEP_THREADS)) ++rp_log2;
-      const int RP = 1 << rp_log2;
-      const int part = tid & (RP - 1);
-      const int cols_per_pass = SWEEP_THREADS >> rp_log2;
-      const unsigned long long* mrow = mask + (size_t)(64 * b) * col_blocks + (b + 1);
-      for (int c = tid >> rp_log2; c < nc; c += cols_per_pass) {
-        unsigned long long acc = 0;
-        int ri = part;
-        for (; ri + 7 * RP < kc; ri += 8 * RP) {
-          unsigned long long w[8];
+      if (lane == 0) { s_kept[b & 1] = K; s_count = count + take; }
+    } else if (b > 0) {
+      // ---- OR the kept rows of block b-1 into the removal bitmap of column blocks >= b+1
+      // (column b was handled by warp 0's `fast`).  (kept row, column) pairs are spread over
+      // warps 1..31 -- RP row parts x columns -- and every thread issues its loads eight at a
+      // time before using them.
+      const int pb = b - 1;
+      const unsigned long long K = s_kept[pb & 1];
+      const int nc = col_blocks - (pb + 2);
+      if (nc > 0 && K != 0ull) {
+        const int* rows = s_rows[pb & 1];
+        const int t = tid - 32;
+        const int kc = __popcll(K);
+        int rp_log2 = 0;
+        while (rp_log2 < 5 && ((nc << (rp_log2 + 1)) <= SWEEP_OR_THREADS)) ++rp_log2;
+        const int RP = 1 << rp_log2;
+        const int part = t & (RP - 1);
+        const int cols_per_pass = SWEEP_OR_THREADS >> rp_log2;
+        const unsigned long long* mrow = mask + (size_t)(64 * pb) * col_blocks + (pb + 2);
+        for (int c = t >> rp_log2; c < nc; c += cols_per_pass) {
+          unsigned long long acc = 0;
+          int ri = part;
+          for (; ri + 7 * RP < kc; ri += 8 * RP) {
+            unsigned long long w[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) w[u] = mrow[(size_t)s_rows[ri + u * RP] * col_blocks + c];
-          acc |= ((w[0] | w[1]) | (w[2] | w[3])) | ((w[4] | w[5]) | (w[6] | w[7]));
-        }
-        for (; ri + 3 * RP < kc; ri += 4 * RP) {
-          const unsigned long long w0 = mrow[(size_t)s_rows[ri] * col_blocks + c];
-          const unsigned long long w1 = mrow[(size_t)s_rows[ri + RP] * col_blocks + c];
-          const unsigned long long w2 = mrow[(size_t)s_rows[ri + 2 * RP] * col_blocks + c];
-          const unsigned long long w3 = mrow[(size_t)s_rows[ri + 3 * RP] * col_blocks + c];
-          acc |= (w0 | w1) | (w2 | w3);
-        }
-        for (; ri < kc; ri += RP) acc |= mrow[(size_t)s_rows[ri] * col_blocks + c];
-        if (acc != 0ull) {
-          if (RP == 1) remv[b + 1 + c] |= acc;
-          else atomicOr(&remv[b + 1 + c], acc);
+            for (int u = 0; u < 8; ++u) w[u] = mrow[(size_t)rows[ri + u * RP] * col_blocks + c];
+            acc |= ((w[0] | w[1]) | (w[2] | w[3])) | ((w[4] | w[5]) | (w[6] | w[7]));
+          }
+          for (; ri + 3 * RP < kc; ri += 4 * RP) {
+            const unsigned long long w0 = mrow[(size_t)rows[ri] * col_blocks + c];
+            const unsigned long long w1 = mrow[(size_t)rows[ri + RP] * col_blocks + c];
+            const unsigned long long w2 = mrow[(size_t)rows[ri + 2 * RP] * col_blocks + c];
+            const unsigned long long w3 = mrow[(size_t)rows[ri + 3 * RP] * col_blocks + c];
+            acc |= (w0 | w1) | (w2 | w3);
+          }
+          for (; ri < kc; ri += RP) acc |= mrow[(size_t)rows[ri] * col_blocks + c];
+          if (acc != 0ull) {
+            if (RP == 1) remv[pb + 2 + c] |= acc;
+            else atomicOr(&remv[pb + 2 + c], acc);
+          }
         }
       }
     }
     __syncthreads();
+    if (s_count >= limit) break;
   }
   if (tid == 0) *num_keep = s_count;
 }
@@ -431,15 +466,15 @@ int run_nms(const float* dets, int N, int stride, double thresh, int mode, int m
   const Thresh th = make_thresh(thresh, mode);
   dim3 mgrid((unsigned)col_blocks, (unsigned)ceil_div(N, MASK_ROWS));
   nms_mask_kernel<<<mgrid, MASK_ROWS, 0, s>>>(boxes, areas, N, col_blocks, th, mask, status);
-  // Large N: the sweep runs on a cluster of 8 CTAs.  Measured on B200 (thr 0.7, single CTA ->
-  // cluster): boxes that mostly survive 6 000: 0.445 -> 0.396 ms, 20 000: 1.79 -> 1.44,
-  // 50 000: 9.2 -> 5.9, 100 000: 29.4 -> 16.6; RPN-like clustered boxes (few survivors, the
-  // per-block barrier is pure latency) 6 000: 0.326 -> 0.349, 20 000: 1.06 -> 1.21, 50 000:
-  // 3.93 -> 4.09, 100 000: 12.67 -> 12.59.  Default: cluster from N = 32 768, where it no
-  // longer loses on either kind.  WSSDL_NMS_SWEEP_CLUSTER=0|1 overrides.
+  // Very large N: the sweep runs on a cluster of 8 CTAs.  Measured on B200 (thr 0.7, pipelined
+  // single CTA / cluster): boxes that mostly survive 6 000: 0.363 / 0.403 ms, 20 000: 1.39 /
+  // 1.44, 50 000: 6.59 / 5.90, 100 000: 21.7 / 16.6; RPN-like clustered boxes (few survivors:
+  // the per-block barrier is pure latency) 6 000: 0.272 / 0.370, 20 000: 0.886 / 1.18, 50 000:
+  // 3.45 / 4.18, 100 000: 11.8 / 12.6.  Default: cluster from N = 65 536.
+  // WSSDL_NMS_SWEEP_CLUSTER=0|1 overrides.
   constexpr int SWEEP_CS = 8;
   const char* cenv = getenv("WSSDL_NMS_SWEEP_CLUSTER");
-  const bool clustered = cenv ? (cenv[0] == '1') : (col_blocks >= 512);
+  const bool clustered = cenv ? (cenv[0] == '1') : (col_blocks >= 1024);
   const size_t sweep_smem = sizeof(unsigned long long) * (size_t)col_blocks;
   if (sweep_smem > 48 * 1024) {                     // N > 393 216: opt in to the large carve-out
     if (clustered)
