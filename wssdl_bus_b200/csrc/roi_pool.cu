@@ -4,20 +4,29 @@
 // (roi_pooling_layer/roi_pooling_op.cc:137-196, :383-458); CUDA twin
 // (roi_pooling_op_gpu.cu.cc:19-85) selectable as bin_mode GPU_CEIL.
 //
-// Forward design (HBM-write bound: 8 B written per output element, the feature map is
-// L2 resident):
+// Forward: HBM-write bound by the roofline (8 B written per output element against 4 B read per
+// map element), three kernels with identical results, picked by shape in choose_fwd():
+//   band   (roi_pool_fwd_band_kernel)  32-channel slice of overlapping row bands of the map in
+//          shared memory: conflict-free 128 B cells, full-line stores.  The detector's shapes.
+//   direct (roi_pool_fwd_kernel)       one CTA per (roi, ph) output row reading the L2-resident
+//          map.  Big bins, grids that the band kernel would split into a few ragged waves.
+//   tiled  (roi_pool_fwd_tiled_kernel) 16-channel slice of the whole map in shared memory.
+//          C % 32 != 0.
+// Common to all: threads run along C (channels, not cells, are the parallel axis in NHWC), each
+// thread scans its bin h-major / w-minor with strict '>' exactly like roi_pooling_op.cc:184-191,
+// so ties (post-ReLU zeros) resolve to the first cell with no cross-lane reduction; outputs are
+// never re-read and leave as streaming stores.
+//
+// Direct kernel design:
 //   - one CTA per (roi, ph) output row; threads run along C in float4 lanes, so every
 //     feature-map cell is read as one fully coalesced 16 B/lane segment and every output
 //     row (PW*C floats + PW*C ints) is written as contiguous 128-bit streaming stores;
 //   - the RoI geometry (4 rounds, 2 IEEE divisions) is computed once per thread and
 //     reused for all PW bins instead of once per output element as in the reference;
-//   - each thread scans its bin h-major / w-minor with strict '>' exactly like
-//     roi_pooling_op.cc:184-191, so ties (post-ReLU zeros) resolve to the first cell with
-//     no cross-lane reduction needed: channels, not cells, are the parallel axis in NHWC;
-//   - CPU_TRUNC bins never overlap, so a cell is read once per RoI: there is no reuse for
-//     shared memory to capture; loads go through the read-only path (ld.global.nc) and
-//     the outputs, never re-read by this kernel, use st.global.cs so they do not evict
-//     the feature map from L2.
+//   - CPU_TRUNC bins never overlap, so a cell is read once per RoI and nothing is reused
+//     inside one RoI (the reuse the shared-memory kernels capture is ACROSS the RoIs of an
+//     image); loads go through the read-only path (ld.global.nc) and the outputs use
+//     st.global.cs so they do not evict the feature map from L2.
 #include <stdlib.h>
 #include <string.h>
 
