@@ -244,3 +244,71 @@ def test_voc_eval_restatement_hand_cases(oracle_mod):
     assert (ni, nok, nfp, per_img) == (2, 0, 1, [1, 0]) and ap == 0
     assert L.voc_eval_arrays([], [], np.zeros((0, 4)), gt, dif)[2] == -1
     assert abs(L.voc_ap(np.array([.5, 1.]), np.array([1., .5]), False) - 0.75) < 1e-12
+
+
+def _roi_pool_fwd_python(bottom, rois, PH, PW, scale, gpu_bins):
+    """Second, independent restatement of the RoiPool body in plain Python loops with numpy
+    float32 scalars (roi_pooling_op.cc:141-195; gpu_bins: roi_pooling_op_gpu.cu.cc:51-58).
+    Only for tiny cases: it pins the C restatement the GPU parity tests use."""
+    import math
+    f32 = np.float32
+    B, H, W, C = bottom.shape
+    R = rois.shape[0]
+    top = np.zeros((R, PH, PW, C), np.float32)
+    arg = np.zeros((R, PH, PW, C), np.int32)
+
+    def c_round(x):                                   # C round(): half away from zero
+        x = float(x)
+        return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+    for n in range(R):
+        r = rois[n]
+        b = int(r[0])
+        sw, sh = c_round(f32(r[1]) * f32(scale)), c_round(f32(r[2]) * f32(scale))
+        ew, eh = c_round(f32(r[3]) * f32(scale)), c_round(f32(r[4]) * f32(scale))
+        roi_w, roi_h = max(ew - sw + 1, 1), max(eh - sh + 1, 1)
+        bin_h, bin_w = f32(roi_h) / f32(PH), f32(roi_w) / f32(PW)
+        for ph in range(PH):
+            for pw in range(PW):
+                if gpu_bins:
+                    hs, he = math.floor(f32(ph) * bin_h), math.ceil(f32(ph + 1) * bin_h)
+                    ws, we = math.floor(f32(pw) * bin_w), math.ceil(f32(pw + 1) * bin_w)
+                else:                                 # static_cast<int> BEFORE floor / ceil
+                    hs, he = int(f32(ph) * bin_h), int(f32(ph + 1) * bin_h)
+                    ws, we = int(f32(pw) * bin_w), int(f32(pw + 1) * bin_w)
+                hs, he = min(max(hs + sh, 0), H), min(max(he + sh, 0), H)
+                ws, we = min(max(ws + sw, 0), W), min(max(we + sw, 0), W)
+                empty = he <= hs or we <= ws
+                for c in range(C):
+                    maxval, maxidx = (f32(0) if empty else f32(-3.4028234663852886e38)), -1
+                    for h in range(hs, he):
+                        for w in range(ws, we):
+                            v = bottom[b, h, w, c]
+                            if v > maxval:
+                                maxval, maxidx = v, (h * W + w) * C + c
+                    top[n, ph, pw, c], arg[n, ph, pw, c] = maxval, maxidx
+    return top, arg
+
+
+@pytest.mark.parametrize("gpu_bins", [False, True])
+def test_roi_pool_fwd_c_restatement_equals_python_restatement(oracle_mod, gpu_bins):
+    """Two restatements of roi_pooling_op.cc written independently (C with float/int casts,
+    Python with numpy float32 scalars) must agree bit for bit on random and adversarial RoIs:
+    the op itself cannot be built here (TensorFlow 1.x headers), so this is the strongest pin
+    available for the RoI-pool oracle besides the hand-derived bin tables."""
+    from wssdl_bus_b200 import synthetic as syn
+    B, H, W, C = 2, 13, 17, 3
+    bottom = syn.feature_map(70, B, H, W, C)
+    bottom[0, 2:4, 3:6] = -np.inf
+    bottom[1, 0, 0, :] = np.nan
+    rois = np.concatenate([
+        syn.rois_for_pool(71, 40, B, im_w=W * 16, im_h=H * 16),
+        syn.adversarial_rois(B, W, H)[:, :],
+        np.array([[0, -37.0, -90.0, 500.0, 700.0], [1, 8.0, 24.0, 8.0, 24.0],
+                  [1, 100.0, 60.0, 20.0, 10.0]], np.float32)])
+    for PH, PW in ((7, 7), (3, 5), (1, 1), (14, 14)):
+        want_t, want_a = _roi_pool_fwd_python(bottom, rois, PH, PW, 1 / 16., gpu_bins)
+        got_t, got_a = oracle_mod.clib.roi_pool_fwd(bottom, rois, PH, PW, 1 / 16.,
+                                                    bin_mode=1 if gpu_bins else 0)
+        assert np.array_equal(got_a, want_a), (PH, PW)
+        assert np.array_equal(got_t, want_t, equal_nan=True), (PH, PW)
