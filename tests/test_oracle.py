@@ -312,3 +312,72 @@ def test_roi_pool_fwd_c_restatement_equals_python_restatement(oracle_mod, gpu_bi
                                                     bin_mode=1 if gpu_bins else 0)
         assert np.array_equal(got_a, want_a), (PH, PW)
         assert np.array_equal(got_t, want_t, equal_nan=True), (PH, PW)
+
+
+def _roi_pool_bwd_python(top_diff, argmax, rois, shape, scale):
+    """Independent restatement of the RoiPoolGrad body (roi_pooling_op.cc:387-457) in plain
+    Python with numpy float32 scalars: a gather over input cells, float32 accumulation in
+    (roi, ph, pw) order."""
+    import math
+    f32 = np.float32
+    B, H, W, C = shape
+    R, PH, PW, _ = top_diff.shape
+    out = np.zeros(shape, np.float32)
+
+    def c_round(x):
+        x = float(x)
+        return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+    geo = []
+    for r in rois:
+        sw, sh = c_round(f32(r[1]) * f32(scale)), c_round(f32(r[2]) * f32(scale))
+        ew, eh = c_round(f32(r[3]) * f32(scale)), c_round(f32(r[4]) * f32(scale))
+        bin_h = f32(max(eh - sh + 1, 1)) / f32(PH)
+        bin_w = f32(max(ew - sw + 1, 1)) / f32(PW)
+        geo.append((int(r[0]), sw, sh, ew, eh, bin_h, bin_w))
+    for n in range(B):
+        for h in range(H):
+            for w in range(W):
+                for c in range(C):
+                    grad = f32(0)
+                    for roi_n, (b, sw, sh, ew, eh, bin_h, bin_w) in enumerate(geo):
+                        if n != b or not (sw <= w <= ew and sh <= h <= eh):
+                            continue
+                        phs = math.floor(f32(h - sh) / bin_h)
+                        phe = math.ceil(f32(h - sh + 1) / bin_h)
+                        pws = math.floor(f32(w - sw) / bin_w)
+                        pwe = math.ceil(f32(w - sw + 1) / bin_w)
+                        phs, phe = min(max(phs, 0), PH), min(max(phe, 0), PH)
+                        pws, pwe = min(max(pws, 0), PW), min(max(pwe, 0), PW)
+                        for ph in range(phs, phe):
+                            for pw in range(pws, pwe):
+                                if argmax[roi_n, ph, pw, c] == (h * W + w) * C + c:
+                                    grad = f32(grad + top_diff[roi_n, ph, pw, c])
+                    out[n, h, w, c] = grad
+    return out
+
+
+def test_roi_pool_bwd_c_restatement_equals_python_restatement(oracle_mod):
+    """Same idea as the forward cross-check, for RoiPoolGrad: the C restatement (both its
+    literal gather and its fast form) against an independent Python restatement, bit for bit
+    (the accumulation order is the reference's, so float32 sums agree exactly)."""
+    clib = oracle_mod.clib
+    rng = np.random.default_rng(81)
+    B, H, W, C, PH, PW = 2, 7, 9, 2, 3, 3
+    bottom = syn.feature_map(82, B, H, W, C)
+    rois = np.concatenate([
+        syn.rois_for_pool(83, 14, B, im_w=W * 16, im_h=H * 16),
+        np.array([[0, -20.0, -30.0, 200.0, 150.0], [1, 16.0, 16.0, 16.0, 16.0],
+                  [1, 100.0, 60.0, 20.0, 10.0], [0, 0.0, 0.0, 47.0, 47.0]], np.float32)])
+    for mode in (clib.CPU_TRUNC, clib.GPU_CEIL):
+        top, arg = clib.roi_pool_fwd(bottom, rois, PH, PW, 1 / 16., bin_mode=mode)
+        g = rng.standard_normal(top.shape).astype(np.float32)
+        want = _roi_pool_bwd_python(g, arg, rois, bottom.shape, 1 / 16.)
+        for literal in (True, False):
+            got = clib.roi_pool_bwd(g, arg, rois, bottom.shape, 1 / 16., literal=literal)
+            assert np.array_equal(got, want), (mode, literal)
+    # arbitrary argmax (never produced by a forward): the gather's feasibility tests decide
+    arg = rng.integers(-1, H * W * C, size=(rois.shape[0], PH, PW, C)).astype(np.int32)
+    g = rng.standard_normal(arg.shape).astype(np.float32)
+    want = _roi_pool_bwd_python(g, arg, rois, bottom.shape, 1 / 16.)
+    assert np.array_equal(clib.roi_pool_bwd(g, arg, rois, bottom.shape, 1 / 16., literal=True), want)
