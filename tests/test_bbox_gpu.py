@@ -114,3 +114,58 @@ def test_anchor_and_proposal_target_layers_match_oracle(oracle_mod):
     assert np.array_equal(r, orois) and np.array_equal(l.ravel(), ol)
     np.testing.assert_allclose(t, ot, rtol=RTOL, atol=1e-6)
     assert np.array_equal(iw2, oiw) and np.array_equal(ow2, (oiw > 0).astype(np.float32))
+
+
+def test_target_layers_match_reference_generated_golden(monkeypatch):
+    """The drop-in layers (device IoU / labels / targets, host npr.choice) against fixtures
+    produced by the reference's OWN anchor_target_layer[_joint] / proposal_target_layer /
+    proposal_layer code (tests/golden/make_layers_golden.py), numpy.random seeded the same:
+    labels, sampled RoIs and weights bit-exact, regression targets within 1e-5."""
+    import os
+    import numpy.random as npr
+    from wssdl_bus_b200.fast_rcnn.config import cfg
+    from wssdl_bus_b200.rpn_msr import anchor_target_layer_tf_bus as atl
+    from wssdl_bus_b200.rpn_msr import proposal_target_layer_tf_bus as ptl
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_layers_golden.npz"))
+    if str(g["numpy_version"]) != np.__version__:
+        pytest.skip("fixture made with numpy %s" % g["numpy_version"])
+    names = ("labels", "targets", "inside", "outside")
+
+    def check(got, prefix):
+        assert np.array_equal(got[0], g[prefix + "labels"])
+        np.testing.assert_allclose(got[1], g[prefix + "targets"], rtol=RTOL, atol=1e-6)
+        assert np.array_equal(got[2], g[prefix + "inside"])
+        np.testing.assert_allclose(got[3], g[prefix + "outside"], rtol=1e-6)
+
+    # joint layer: 2 supervised + 1 weakly supervised image on a 12x16 map
+    monkeypatch.setattr(cfg.TRAIN, "IMS_PER_BATCH", 2)
+    monkeypatch.setattr(cfg.TRAIN, "WS_IMS_PER_BATCH", 1)
+    npr.seed(1234)
+    got = atl.anchor_target_layer_joint(np.zeros((3, 12, 16, 18), np.float32), g["at_gt"],
+                                        g["at_num"], g["prop_info"], None, True, [16, ],
+                                        [8, 16, 32], "SNUBH")
+    check(got, "at_joint_")
+    # plain layer, 38x50 map: SNUBH, the general branch (bg draw happens), SNUBH with a
+    # background box over most of the image (bg draw happens)
+    score = np.zeros((1, 38, 50, 18), np.float32)
+    for seed, prefix, gt, num, ds in ((4321, "at1_", g["at1_gt"], g["at1_num"], "SNUBH"),
+                                      (2468, "at2_", g["at1_gt"], g["at1_num"], "VOC"),
+                                      (1357, "at3_", g["at3_gt"], g["at3_num"], "SNUBH")):
+        npr.seed(seed)
+        check(atl.anchor_target_layer(score, gt, num, g["at1_info"], None, [16, ], [8, 16, 32], ds),
+              prefix)
+    # proposal target layer on the reference's own TRAIN proposals (573 RoIs of 2 images)
+    monkeypatch.setattr(cfg.TRAIN, "WS_IMS_PER_BATCH", 0)
+    npr.seed(777)
+    r, l, t, iw, ow = ptl.proposal_target_layer(g["prop_blob_train"], g["at_gt"], g["at_num"], 3,
+                                                True, False)
+    assert np.array_equal(r, g["ptl_rois"]) and np.array_equal(l, g["ptl_labels"])
+    np.testing.assert_allclose(t, g["ptl_targets"], rtol=RTOL, atol=1e-6)
+    assert np.array_equal(iw, g["ptl_inside"]) and np.array_equal(ow, g["ptl_outside"])
+    # proposal layer (drop-in signature): same RoIs as the reference within the decode
+    # tolerance (np.exp vs correctly rounded exp), same count
+    from wssdl_bus_b200.rpn_msr.proposal_layer_tf_bus import proposal_layer
+    blob = proposal_layer(g["prop_cls"], g["prop_reg"], g["prop_info"], False, False)
+    assert blob.shape == g["prop_blob_test"].shape
+    np.testing.assert_allclose(blob, g["prop_blob_test"], rtol=RTOL, atol=1e-3)
+    del names

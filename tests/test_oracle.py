@@ -381,3 +381,90 @@ def test_roi_pool_bwd_c_restatement_equals_python_restatement(oracle_mod):
     g = rng.standard_normal(arg.shape).astype(np.float32)
     want = _roi_pool_bwd_python(g, arg, rois, bottom.shape, 1 / 16.)
     assert np.array_equal(clib.roi_pool_bwd(g, arg, rois, bottom.shape, 1 / 16., literal=True), want)
+
+
+# ---- glue layers against fixtures produced by the reference's own layer code
+# (tests/golden/make_layers_golden.py runs rpn_msr/*_tf_bus.py from /root/reference under a
+# mechanical py2->py3 shim; inputs are seeded, numpy.random is seeded before every call)
+@pytest.fixture(scope="module")
+def layers_golden():
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_layers_golden.npz")
+    g = np.load(path)
+    if str(g["numpy_version"]) != np.__version__:
+        pytest.skip("fixture made with numpy %s (np.exp / RandomState streams are only "
+                    "guaranteed identical on the same numpy)" % g["numpy_version"])
+    return g
+
+
+def test_proposal_layer_restatement_equals_reference_output(oracle_mod, layers_golden):
+    g, L = layers_golden, oracle_mod.layers
+    cls, reg, info = g["prop_cls"], g["prop_reg"], g["prop_info"]
+    assert np.array_equal(L.proposal_layer(cls, reg, info, is_training=False), g["prop_blob_test"])
+    assert np.array_equal(L.proposal_layer(cls, reg, info, is_training=True), g["prop_blob_train"])
+    c1 = syn.rpn_outputs(int(g["prop_c1_seed"]), 1, 38, 50, 9)
+    blob = L.proposal_layer(c1[0], c1[1], c1[2], is_training=False)
+    assert blob.shape == (300, 5) and np.array_equal(blob, g["prop_c1_blob_test"])
+
+
+def _anchor_layer_from_blocks(L, H, W, gts, infos, seed, dataset="SNUBH"):
+    """anchor_target_layer[_joint] output layout (anchor_target_layer_tf_bus.py:568-611)
+    assembled from the oracle's per-image blocks, with numpy.random as the injected RNG."""
+    A = 9
+    np.random.seed(seed)
+    outs = [[], [], [], []]
+    for gt, info in zip(gts, infos):
+        lab = L.anchor_labels(H, W, gt, info, dataset=dataset)
+        labels, targets, inside, outside = L.anchor_targets_from_labels(lab, np.random)
+        outs[0].append(labels.reshape((1, H, W, A)).transpose(0, 3, 1, 2).reshape((1, 1, A * H, W)))
+        for k, v in ((1, targets), (2, inside), (3, outside)):
+            outs[k].append(v.reshape((1, H, W, A * 4)).transpose(0, 3, 1, 2))
+    return [np.concatenate(o) for o in outs]
+
+
+def test_anchor_target_layer_restatement_equals_reference_output(oracle_mod, layers_golden):
+    g, L = layers_golden, oracle_mod.layers
+    # joint layer: two supervised images + one weakly supervised image (labels -1, zeros)
+    gt, num, info = g["at_gt"], g["at_num"], g["prop_info"]
+    got = _anchor_layer_from_blocks(L, 12, 16, [gt[i, :num[i]] for i in range(2)], info, 1234)
+    for k, name in enumerate(("labels", "targets", "inside", "outside")):
+        want = g["at_joint_" + name]
+        assert np.array_equal(got[k], want[:2]), name
+        assert np.all(want[2] == (-1 if name == "labels" else 0))
+    assert (got[0] == 1).sum() > 0 and (got[0] == 0).sum() > 0
+    # plain layer at the full 38x50 map: fg/bg subsampling through npr.choice
+    gt1, num1 = g["at1_gt"], g["at1_num"]
+    got = _anchor_layer_from_blocks(L, 38, 50, [gt1[0, :num1[0]]], g["at1_info"], 4321)
+    for k, name in enumerate(("labels", "targets", "inside", "outside")):
+        assert np.array_equal(got[k], g["at1_" + name]), name
+    # cases where the npr.choice draws happen (256 = RPN_BATCHSIZE labelled anchors remain):
+    # the general (non-SNUBH) branch, and SNUBH with a background box over most of the image
+    got = _anchor_layer_from_blocks(L, 38, 50, [gt1[0, :num1[0]]], g["at1_info"], 2468, dataset="VOC")
+    for k, name in enumerate(("labels", "targets", "inside", "outside")):
+        assert np.array_equal(got[k], g["at2_" + name]), name
+    assert (got[0] == 0).sum() + (got[0] == 1).sum() == 256 and (got[0] == 0).sum() > 200
+    gt3, num3 = g["at3_gt"], g["at3_num"]
+    got = _anchor_layer_from_blocks(L, 38, 50, [gt3[0, :num3[0]]], g["at1_info"], 1357)
+    for k, name in enumerate(("labels", "targets", "inside", "outside")):
+        assert np.array_equal(got[k], g["at3_" + name]), name
+    assert (got[0] == 0).sum() + (got[0] == 1).sum() == 256 and (got[0] == 0).sum() > 200
+
+
+def test_proposal_target_layer_restatement_equals_reference_output(oracle_mod, layers_golden):
+    g, L = layers_golden, oracle_mod.layers
+    rois_in, gt, num = g["prop_blob_train"], g["at_gt"], g["at_num"]
+    np.random.seed(777)
+    got = [[], [], [], []]
+    for i in range(2):
+        all_rois = rois_in[rois_in[:, 0] == i]
+        t_gt = gt[i, :num[i]]
+        fg_gt = t_gt[:int(np.sum(t_gt[:, 4] != 0))]
+        # GT boxes join the candidates (proposal_target_layer_tf_bus.py:45-50)
+        extra = np.hstack((np.full((fg_gt.shape[0], 1), i, fg_gt.dtype), fg_gt[:, :-1]))
+        all_rois = np.vstack((all_rois, extra))
+        labels, rois, targets, inside, _ = L.sample_rois(all_rois, fg_gt, 32, 128, 3, np.random)
+        for k, v in enumerate((rois, labels.reshape(-1, 1), targets, inside)):
+            got[k].append(v)
+    got = [np.concatenate(v) for v in got]
+    for k, name in enumerate(("rois", "labels", "targets", "inside")):
+        assert np.array_equal(got[k], g["ptl_" + name]), name
+    assert np.array_equal((got[3] > 0).astype(np.float32), g["ptl_outside"])
