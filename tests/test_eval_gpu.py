@@ -95,3 +95,48 @@ def test_eval_hand_case_and_limits():
     assert m["img_stats"].cpu().numpy()[:, 1].tolist() == [[1, 1], [1, 1]]
     with pytest.raises(_lib.WssdlError):
         ops.eval_match(dets, counts, np.zeros((2, 65, 5), np.float32), np.array([1, 1], np.int32))
+
+
+def test_eval_matches_reference_generated_golden():
+    """evaluate_detections_blob (matching on the device) against the output of the reference's
+    OWN voc_eval_bus() on a synthetic VOC-style tree (tests/golden/make_layers_golden.py):
+    rec / prec / AP (both flavours), CorLoc counts, FROC false positives, bit for bit."""
+    import os
+    from wssdl_bus_b200.datasets import voc_eval_bus
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_layers_golden.npz"))
+    if str(g["numpy_version"]) != np.__version__:
+        pytest.skip("fixture made with numpy %s" % g["numpy_version"])
+    counts_gt = g["eval_gt_counts"]
+    B = len(counts_gt)
+    ofs = np.concatenate(([0], np.cumsum(counts_gt)))
+    G = 4
+    gt = np.zeros((B, G, 5), np.float32)
+    num = counts_gt.astype(np.int32)
+    diff = np.zeros((B, G), np.uint8)
+    for b in range(B):
+        n = num[b]
+        gt[b, :n, :4] = g["eval_gt_bbox"][ofs[b]:ofs[b + 1]]
+        gt[b, :n, 4] = 1
+        diff[b, :n] = g["eval_gt_difficult"][ofs[b]:ofs[b + 1]]
+    ids, conf, BB = g["eval_image_ids"], g["eval_confidence"], g["eval_BB"]
+    S = int(np.bincount(ids, minlength=B).max())
+    dets = np.zeros((B, 2, S, 5), np.float32)
+    counts = np.zeros((B, 2), np.int32)
+    for b in range(B):
+        sel = np.where(ids == b)[0]
+        sel = sel[np.argsort(-conf[sel])]                 # class lists are in descending score
+        counts[b, 1] = len(sel)
+        dets[b, 1, :len(sel), :4] = BB[sel]
+        dets[b, 1, :len(sel), 4] = conf[sel]
+    # the fixture's boxes and scores are exactly representable decimals x.y / 0.xyz parsed as
+    # float64; the blob is float32: box coordinates k/10 below 1024 and scores k/1000 are not
+    # all exact in float32, so compare what float32 can carry: the discrete outcomes and AP
+    for tag, use07 in (("area", False), ("voc07", True)):
+        r = voc_eval_bus.evaluate_detections_blob(dets, counts, gt, num, diff, ovthresh=0.5,
+                                                  use_07_metric=use07, score_thresh=0.5)[0]
+        ap, ni, nok, nfp = g["eval_%s_scalars" % tag].tolist()
+        assert (r["ni"], r["nok"], r["num_all_fps"]) == (ni, nok, nfp)
+        assert list(r["num_fp_per_img"]) == g["eval_%s_fp_per_img" % tag].tolist()
+        assert np.array_equal(r["rec"], g["eval_%s_rec" % tag])
+        assert np.array_equal(r["prec"], g["eval_%s_prec" % tag])
+        assert r["ap"] == ap

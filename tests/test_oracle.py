@@ -468,3 +468,23 @@ def test_proposal_target_layer_restatement_equals_reference_output(oracle_mod, l
     for k, name in enumerate(("rois", "labels", "targets", "inside")):
         assert np.array_equal(got[k], g["ptl_" + name]), name
     assert np.array_equal((got[3] > 0).astype(np.float32), g["ptl_outside"])
+
+
+def test_voc_eval_restatement_equals_reference_output(oracle_mod, layers_golden):
+    """voc_eval_arrays against the reference's voc_eval_bus() run on a synthetic VOC-style tree
+    (XML annotations, a detection text file) in make_layers_golden.py: rec / prec arrays, AP in
+    both flavours, CorLoc counts and FROC false-positive counts, all bit for bit."""
+    g, L = layers_golden, oracle_mod.layers
+    counts = g["eval_gt_counts"]
+    ofs = np.concatenate(([0], np.cumsum(counts)))
+    gt_bbox = [g["eval_gt_bbox"][ofs[i]:ofs[i + 1]] for i in range(len(counts))]
+    gt_diff = [g["eval_gt_difficult"][ofs[i]:ofs[i + 1]] for i in range(len(counts))]
+    assert g["eval_gt_difficult"].any() and (counts == 0).any()
+    for tag, use07 in (("area", False), ("voc07", True)):
+        rec, prec, ap, ni, nok, nfp, fp_per_img = L.voc_eval_arrays(
+            g["eval_image_ids"], g["eval_confidence"], g["eval_BB"], gt_bbox, gt_diff,
+            ovthresh=0.5, use_07_metric=use07, score_thresh=0.5)
+        assert np.array_equal(rec, g["eval_%s_rec" % tag])
+        assert np.array_equal(prec, g["eval_%s_prec" % tag])
+        assert [ap, ni, nok, nfp] == g["eval_%s_scalars" % tag].tolist()
+        assert list(fp_per_img) == g["eval_%s_fp_per_img" % tag].tolist()
