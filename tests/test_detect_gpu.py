@@ -91,3 +91,38 @@ def test_limits_and_empty():
     with pytest.raises(_lib.WssdlError):
         ops.detect_postprocess(np.zeros((2000, 5), np.float32), np.zeros((2000, 3), np.float32),
                                np.zeros((2000, 12), np.float32), meta)
+
+
+def test_postprocess_matches_reference_generated_golden(monkeypatch):
+    """The drop-in wrappers and the fused kernel against the reference's own code blocks
+    (fast_rcnn/test_bus.py:207-223, :359-401 executed as fragments by
+    tests/golden/make_layers_golden.py): regressed boxes within 1e-5, per-class NMS lists /
+    class-agnostic pass / max_per_image cap bit for bit on the reference's boxes."""
+    import os
+    from wssdl_bus_b200.fast_rcnn import test_bus
+    from wssdl_bus_b200.fast_rcnn.config import cfg
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_layers_golden.npz"))
+    if str(g["numpy_version"]) != np.__version__:
+        pytest.skip("fixture made with numpy %s" % g["numpy_version"])
+    im_h, im_w, im_scale = g["det_meta"]
+    pb = test_bus.detect_boxes(g["det_rois"], g["det_deltas"], (int(im_h), int(im_w), 3), float(im_scale))
+    np.testing.assert_allclose(pb, g["det_pred_boxes"], rtol=RTOL, atol=1e-3)
+    # discrete steps on the REFERENCE's boxes: exact
+    got = test_bus.postprocess_detections(g["det_scores"], g["det_pred_boxes"])
+    for j in (1, 2):
+        assert np.array_equal(got[j], g["det_plain_cls%d" % j])
+    monkeypatch.setattr(cfg.TEST, "CLS_AGNOSTIC_NMS", True)
+    got = test_bus.postprocess_detections(g["det_scores"], g["det_pred_boxes"], max_per_image=40)
+    for j in (1, 2):
+        assert np.array_equal(got[j], g["det_agnostic_cap_cls%d" % j])
+    monkeypatch.setattr(cfg.TEST, "CLS_AGNOSTIC_NMS", False)
+    # the fused kernel end to end (its own regression): same lists within the box tolerance
+    meta = np.array([[im_h, im_w, im_scale]], np.float32)
+    out = ops.detect_postprocess(g["det_rois"], g["det_scores"], g["det_deltas"], meta,
+                                 roi_stride=300, score_thresh=0.05, nms_thresh=0.3,
+                                 max_per_image=300, cls_agnostic=False)
+    dets, cnt = out["dets"].cpu().numpy(), out["counts"].cpu().numpy()
+    for j in (1, 2):
+        want = g["det_plain_cls%d" % j]
+        assert cnt[0, j] == len(want)
+        np.testing.assert_allclose(dets[0, j, :cnt[0, j]], want, rtol=RTOL, atol=1e-3)

@@ -488,3 +488,22 @@ def test_voc_eval_restatement_equals_reference_output(oracle_mod, layers_golden)
         assert np.array_equal(prec, g["eval_%s_prec" % tag])
         assert [ap, ni, nok, nfp] == g["eval_%s_scalars" % tag].tolist()
         assert list(fp_per_img) == g["eval_%s_fp_per_img" % tag].tolist()
+
+
+def test_detection_postprocess_restatement_equals_reference_output(oracle_mod, layers_golden):
+    """im_detect_boxes / detections_postprocess against the reference's own code blocks
+    (fast_rcnn/test_bus.py:207-223 and :359-401, executed as fragments by
+    make_layers_golden.py): regressed + clipped boxes, per-class NMS 0.3 lists, the
+    class-agnostic pass and the max_per_image cap, bit for bit."""
+    g, L = layers_golden, oracle_mod.layers
+    im_h, im_w, im_scale = g["det_meta"]
+    pred = L.im_detect_boxes(g["det_rois"], g["det_deltas"], (int(im_h), int(im_w), 3), float(im_scale))
+    assert pred.dtype == g["det_pred_boxes"].dtype and np.array_equal(pred, g["det_pred_boxes"])
+    for tag, agnostic, cap in (("plain", False, 300), ("agnostic_cap", True, 40)):
+        out = L.detections_postprocess(g["det_scores"], pred, thresh=0.05, max_per_image=cap,
+                                       cls_agnostic_nms=agnostic)
+        for j in (1, 2):
+            want = g["det_%s_cls%d" % (tag, j)]
+            assert out[j].shape == want.shape and np.array_equal(out[j], want), (tag, j)
+    assert sum(len(g["det_agnostic_cap_cls%d" % j]) for j in (1, 2)) == 40
+    assert len(g["det_plain_cls1"]) > 40
