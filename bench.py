@@ -62,13 +62,17 @@ def make_inputs(n_images, seed0):
 def _cpu_worker(args):
     """One image through the reference's CPU path: proposal_layer (numpy glue + the
     reference's own cpu_nms from oracle/_ref when built, else its C restatement) and the
-    RoiPool CPU kernel restatement, single thread."""
+    RoiPool CPU kernel (the reference's own roi_pooling_op.cc compiled into
+    oracle/_ref/ref_roi_pool.so when built, else its C restatement), single thread."""
     seed, = args
     import oracle
     feat, cls, reg, info = make_inputs(1, seed)
     t0 = time.perf_counter()
     blob = oracle.layers.proposal_layer(cls, reg, info)
-    top, arg = oracle.clib.roi_pool_fwd(feat, blob, CFG["PH"], CFG["PW"], CFG["scale"], threads=1)
+    if oracle.ref.roi_pool_available():
+        top, arg = oracle.ref.roi_pool_fwd(feat, blob, CFG["PH"], CFG["PW"], CFG["scale"], threads=1)
+    else:
+        top, arg = oracle.clib.roi_pool_fwd(feat, blob, CFG["PH"], CFG["PW"], CFG["scale"], threads=1)
     return time.perf_counter() - t0, int(blob.shape[0])
 
 
@@ -78,7 +82,9 @@ def cpu_arm(steps, warmup, sample_images=None):
     import multiprocessing as mp
     import oracle
     oracle.clib.build()
-    kind = "reference" if oracle.ref.available() else "port"
+    kind = "reference" if (oracle.ref.available() and oracle.ref.roi_pool_available()) else "port"
+    roi_kind = ("the reference's own RoiPool CPU kernel (roi_pooling_op.cc compiled unmodified)"
+                if oracle.ref.roi_pool_available() else "C++ RoiPool CPU kernel restatement")
     cores = max(1, len(os.sched_getaffinity(0)))
     n = sample_images or max(cores, 8)
     n = min(n, 256)
@@ -95,9 +101,10 @@ def cpu_arm(steps, warmup, sample_images=None):
     ms_step = 1e3 * float(np.mean(times))
     value = n / (ms_step / 1e3)
     sample = ("%d images/step (of the 256-image C4 batch), image-parallel over %d processes; per "
-              "image: numpy decode/clip/filter/argsort + %s cpu_nms(6000 boxes, 0.7) + C++ "
-              "RoiPool CPU kernel restatement (1 thread); %.2f s/image/core"
-              % (n, min(cores, n), "reference Cython" if kind == "reference" else "C-port", per_image))
+              "image: numpy decode/clip/filter/argsort + %s cpu_nms(6000 boxes, 0.7) + %s "
+              "(1 thread); %.2f s/image/core"
+              % (n, min(cores, n), "reference Cython" if oracle.ref.available() else "C-port",
+                 roi_kind, per_image))
     return dict(value=value, unit=UNIT, cores=min(cores, n), kind=kind, sample=sample), ms_step, n
 
 

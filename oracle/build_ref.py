@@ -22,8 +22,15 @@ importing, because the modules evaluate ``np.float`` / ``np.int`` at run time
 (cpu_nms.pyx:17,29; bbox.pyx:12).  ``thresh`` stays a Python float, so the
 comparison stays ``(double)ovr >= thresh`` exactly as in the reference.
 
-The RoiPool/RoiPoolGrad CPU kernels (roi_pooling_op.cc) need TensorFlow 1.x headers
-and are NOT buildable here; they are restated in ``oracle/roi_pool_ref.c``.
+  ref_roi_pool.so    <- code/lib/roi_pooling_layer/roi_pooling_op.cc, UNMODIFIED: the RoiPool /
+                        RoiPoolGrad CPU kernels.  The file needs the TensorFlow 1.x op framework,
+                        which is not installed; it is compiled against ``oracle/tf_stub`` (a
+                        stand-in that provides containers, status / attribute plumbing and the
+                        registration macros and contains no arithmetic of the op) and linked
+                        with ``oracle/ref_roi_pool_driver.cc`` (binds the op to numpy buffers,
+                        defines Shard() as an even multi-threaded range split).  The kernels
+                        are ALSO restated in ``oracle/hotpath_ref.c`` (faster, plus the CUDA
+                        twin's bins); tests pin the restatement to this build.
 
 Flags: ``-O2`` only; no ``-march=native``, no ``-ffast-math`` and
 ``-ffp-contract=off`` so that x86 FMA contraction can never change a result.
@@ -50,9 +57,47 @@ def have_reference():
     return all(os.path.isfile(os.path.join(REF, p)) for p in MODULES.values())
 
 
+ROI_POOL_SRC = "code/lib/roi_pooling_layer/roi_pooling_op.cc"
+ROI_POOL_SO = os.path.join(OUT, "ref_roi_pool.so")
+
+
 def built():
     suffix = sysconfig.get_config_var("EXT_SUFFIX")
     return all(os.path.isfile(os.path.join(OUT, m + suffix)) for m in MODULES)
+
+
+def roi_pool_built():
+    return os.path.isfile(ROI_POOL_SO)
+
+
+def build_roi_pool(force=False, verbose=False):
+    """g++ the reference's roi_pooling_op.cc (where it lies) against oracle/tf_stub and link it
+    with the driver.  Returns True when oracle/_ref/ref_roi_pool.so exists afterwards."""
+    if roi_pool_built() and not force:
+        return True
+    src = os.path.join(REF, ROI_POOL_SRC)
+    if not os.path.isfile(src):
+        return False
+    os.makedirs(OUT, exist_ok=True)
+    flags = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w",
+             "-I", os.path.join(HERE, "tf_stub"), "-I", os.path.dirname(src)]
+    objs = []
+    for path, obj in ((src, "ref_roi_pooling_op.o"),
+                      (os.path.join(HERE, "ref_roi_pool_driver.cc"), "ref_roi_pool_driver.o")):
+        o = os.path.join(OUT, obj)
+        r = subprocess.run(["g++"] + flags + ["-c", path, "-o", o], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed for %s:\n%s\n%s" % (path, r.stdout, r.stderr))
+        objs.append(o)
+    r = subprocess.run(["g++", "-shared"] + objs + ["-o", ROI_POOL_SO, "-lpthread"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    for o in objs:
+        os.remove(o)
+    if verbose:
+        print("built", ROI_POOL_SO)
+    return True
 
 
 def build(force=False, verbose=False):
@@ -97,3 +142,5 @@ def build(force=False, verbose=False):
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv, verbose=True)
     print("oracle/_ref:", "built" if ok else "reference not present; nothing built")
+    ok = build_roi_pool(force="--force" in sys.argv, verbose=True)
+    print("oracle/_ref/ref_roi_pool.so:", "built" if ok else "reference not present; not built")

@@ -61,3 +61,69 @@ def bbox_overlaps_ui(boxes, query):
     """utils/bbox_ui.pyx:12 (float64 only)."""
     return _load("ref_cython_bbox_ui").bbox_overlaps_ui(
         np.ascontiguousarray(boxes, np.float64), np.ascontiguousarray(query, np.float64))
+
+
+# ---------------------------------------------------------------- RoiPool / RoiPoolGrad
+_roi_lib = None
+
+
+def roi_pool_available():
+    """True when the reference's own roi_pooling_op.cc has been compiled into
+    oracle/_ref/ref_roi_pool.so (oracle/build_ref.py: against oracle/tf_stub)."""
+    from . import build_ref
+    return build_ref.roi_pool_built() or build_ref.build_roi_pool()
+
+
+def _roi():
+    global _roi_lib
+    if _roi_lib is None:
+        import ctypes
+        from . import build_ref
+        if not roi_pool_available():
+            raise ImportError("oracle/_ref/ref_roi_pool.so is not built and /root/reference is absent")
+        L = ctypes.CDLL(build_ref.ROI_POOL_SO)
+        vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        L.ref_roi_pool_fwd.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, cf, ci, vp, vp, ctypes.c_char_p]
+        L.ref_roi_pool_bwd.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, cf, ci, vp, ctypes.c_char_p]
+        _roi_lib = L
+    return _roi_lib
+
+
+def roi_pool_fwd(bottom, rois, pooled_h, pooled_w, spatial_scale, threads=1):
+    """RoiPoolOp<CPUDevice, float>::Compute (roi_pooling_op.cc:88-204), the reference's own
+    object code.  bottom [B,H,W,C] f32, rois [R,5] f32 -> (top f32, argmax i32) [R,PH,PW,C].
+    Batch indices must be inside [0,B): the reference reads out of bounds otherwise."""
+    import ctypes
+    bottom = np.ascontiguousarray(bottom, np.float32)
+    rois = np.ascontiguousarray(rois, np.float32)
+    B, H, W, C = bottom.shape
+    R = rois.shape[0]
+    shape = (R, max(pooled_h, 0), max(pooled_w, 0), C)   # negative sizes: the op itself rejects
+    top = np.empty(shape, np.float32)
+    arg = np.empty(shape, np.int32)
+    err = ctypes.create_string_buffer(256)
+    rc = _roi().ref_roi_pool_fwd(bottom.ctypes.data, rois.ctypes.data, B, H, W, C, R, pooled_h,
+                                 pooled_w, spatial_scale, int(threads), top.ctypes.data,
+                                 arg.ctypes.data, err)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return top, arg
+
+
+def roi_pool_bwd(grad, argmax, rois, bottom_shape, spatial_scale, threads=1):
+    """RoiPoolGradOp<CPUDevice, float>::Compute (roi_pooling_op.cc:333-466) -> [B,H,W,C] f32."""
+    import ctypes
+    grad = np.ascontiguousarray(grad, np.float32)
+    argmax = np.ascontiguousarray(argmax, np.int32)
+    rois = np.ascontiguousarray(rois, np.float32)
+    B, H, W, C = [int(v) for v in bottom_shape]
+    R, PH, PW, _ = grad.shape
+    bottom = np.zeros((B, H, W, C), np.float32)          # only its shape is read
+    out = np.empty((B, H, W, C), np.float32)
+    err = ctypes.create_string_buffer(256)
+    rc = _roi().ref_roi_pool_bwd(bottom.ctypes.data, rois.ctypes.data, argmax.ctypes.data,
+                                 grad.ctypes.data, B, H, W, C, R, PH, PW, spatial_scale,
+                                 int(threads), out.ctypes.data, err)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return out

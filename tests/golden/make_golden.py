@@ -8,9 +8,10 @@ Sources of truth:
   * /root/reference/code/lib/fast_rcnn/bbox_transform.py loaded by file path (unmodified);
   * the anchor table in the header comment of rpn_msr/generate_anchors.py:17-25 (1-based
     MATLAB boxes; the function returns table - 1), typed in below.
-The RoiPool CPU op cannot be built here (TensorFlow headers), so no fixture for it can
-come from the reference; tests/golden/roi_pool_cases.npz instead stores hand-derived bin
-tables -- see tests/test_oracle.py.
+The RoiPool CPU op is pinned differently: oracle/_ref/ref_roi_pool.so is the reference's
+roi_pooling_op.cc compiled against oracle/tf_stub and is compared live in tests/test_oracle.py
+(it travels to the GPU box with the snapshot); the hand-derived bin tables of SURVEY.md
+Appendix A.1 are a second, independent check.
 """
 import importlib.util
 import os

@@ -294,8 +294,9 @@ def _roi_pool_fwd_python(bottom, rois, PH, PW, scale, gpu_bins):
 def test_roi_pool_fwd_c_restatement_equals_python_restatement(oracle_mod, gpu_bins):
     """Two restatements of roi_pooling_op.cc written independently (C with float/int casts,
     Python with numpy float32 scalars) must agree bit for bit on random and adversarial RoIs:
-    the op itself cannot be built here (TensorFlow 1.x headers), so this is the strongest pin
-    available for the RoI-pool oracle besides the hand-derived bin tables."""
+    an independent check next to the reference's own compiled kernel (see
+    test_roi_pool_restatement_equals_reference_kernel), and besides the hand-derived bin tables
+    the only one for the GPU_CEIL bins."""
     from wssdl_bus_b200 import synthetic as syn
     B, H, W, C = 2, 13, 17, 3
     bottom = syn.feature_map(70, B, H, W, C)
@@ -507,3 +508,50 @@ def test_detection_postprocess_restatement_equals_reference_output(oracle_mod, l
             assert out[j].shape == want.shape and np.array_equal(out[j], want), (tag, j)
     assert sum(len(g["det_agnostic_cap_cls%d" % j]) for j in (1, 2)) == 40
     assert len(g["det_plain_cls1"]) > 40
+
+
+# ---- the reference's own RoiPool / RoiPoolGrad CPU kernels (roi_pooling_op.cc compiled
+# unmodified against oracle/tf_stub into oracle/_ref/ref_roi_pool.so)
+def _need_ref_roi_pool(oracle_mod):
+    if not oracle_mod.ref.roi_pool_available():
+        pytest.skip("oracle/_ref/ref_roi_pool.so not built (reference absent)")
+
+
+def test_roi_pool_restatement_equals_reference_kernel(oracle_mod):
+    """The C restatement the GPU parity tests check against (oracle/hotpath_ref.c, CPU_TRUNC
+    bins) versus the object code of the reference's own RoiPoolOp / RoiPoolGradOp: bit for
+    bit on proposal-like, random and adversarial RoIs, several pooled sizes and thread counts,
+    NaN / -inf cells, malformed RoIs."""
+    _need_ref_roi_pool(oracle_mod)
+    clib, ref = oracle_mod.clib, oracle_mod.ref
+    rng = np.random.default_rng(91)
+    for trial, (B, H, W, C) in enumerate([(2, 38, 50, 16), (3, 13, 17, 5), (1, 7, 9, 3), (4, 20, 24, 8)]):
+        bottom = syn.feature_map(92 + trial, B, H, W, C)
+        bottom[0, H // 3:H // 2, W // 4:W // 2] = -np.inf
+        bottom[B - 1, 0, 0, :] = np.nan
+        rois = np.concatenate([syn.rois_for_pool(93 + trial, 60, B, im_w=W * 16, im_h=H * 16),
+                               syn.adversarial_rois(B, W, H)])
+        for PH, PW in ((7, 7), (14, 14), (3, 5), (1, 1)):
+            for threads in (1, 5):
+                top, arg = ref.roi_pool_fwd(bottom, rois, PH, PW, 1 / 16., threads=threads)
+                wt, wa = clib.roi_pool_fwd(bottom, rois, PH, PW, 1 / 16., bin_mode=clib.CPU_TRUNC)
+                assert np.array_equal(arg, wa), (trial, PH, PW)
+                assert np.array_equal(top, wt, equal_nan=True), (trial, PH, PW)
+            g = rng.standard_normal(top.shape).astype(np.float32)
+            want = ref.roi_pool_bwd(g, arg, rois, bottom.shape, 1 / 16., threads=3)
+            for literal in (True, False):
+                got = clib.roi_pool_bwd(g, arg, rois, bottom.shape, 1 / 16., literal=literal)
+                assert np.array_equal(got, want), (trial, PH, PW, literal)
+        # arbitrary argmax tensors (never produced by a forward)
+        arg = rng.integers(-1, H * W * C, size=(rois.shape[0], 3, 3, C)).astype(np.int32)
+        g = rng.standard_normal(arg.shape).astype(np.float32)
+        assert np.array_equal(clib.roi_pool_bwd(g, arg, rois, bottom.shape, 1 / 16., literal=True),
+                              ref.roi_pool_bwd(g, arg, rois, bottom.shape, 1 / 16.))
+
+
+def test_reference_kernel_attribute_checks(oracle_mod):
+    """The op's own checks surface through the driver (roi_pooling_op.cc:73-82)."""
+    _need_ref_roi_pool(oracle_mod)
+    bottom = np.zeros((1, 4, 4, 2), np.float32)
+    with pytest.raises(RuntimeError, match="pooled_height"):
+        oracle_mod.ref.roi_pool_fwd(bottom, np.zeros((1, 5), np.float32), -1, 7, 1 / 16.)

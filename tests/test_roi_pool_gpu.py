@@ -285,3 +285,32 @@ def test_fwd_random_shape_sweep_both_kernels(oracle_mod, monkeypatch):
             ctx = (trial, kern, B, H, W, C, PH, PW, stride, R, mode)
             assert np.array_equal(arg.cpu().numpy(), want_arg), ctx
             assert np.array_equal(top.cpu().numpy(), want_top), ctx
+
+
+def test_fwd_bwd_against_the_reference_kernel_itself(oracle_mod, fwd_kernel):
+    """Every forward kernel and both backward modes against the object code of the
+    reference's own RoiPoolOp / RoiPoolGradOp (roi_pooling_op.cc compiled unmodified into
+    oracle/_ref/ref_roi_pool.so, see oracle/build_ref.py): BASELINE shapes C1 (300 proposal-like
+    RoIs, 512 channels) forward, C2 (128 RoIs) forward + backward, plus adversarial RoIs."""
+    if not oracle_mod.ref.roi_pool_available():
+        pytest.skip("oracle/_ref/ref_roi_pool.so not built (reference absent)")
+    ref = oracle_mod.ref
+    c = syn.C1
+    bottom = syn.feature_map(50, 1, c["H"], c["W"], c["C"])
+    rois = np.concatenate([syn.rois_for_pool(51, 300), syn.adversarial_rois(1, c["W"], c["H"])])
+    want_t, want_a = ref.roi_pool_fwd(bottom, rois, 7, 7, c["scale"], threads=16)
+    top, arg = ops.roi_pool_forward(bottom, rois, 7, 7, c["scale"])
+    assert np.array_equal(arg.cpu().numpy(), want_a) and np.array_equal(top.cpu().numpy(), want_t)
+    # C2: 128 sampled RoIs, forward + backward on a 128-channel slice of the map (the
+    # reference's gather is O(cells x RoIs))
+    b2 = np.ascontiguousarray(bottom[..., :128])
+    r2 = rois[:128]
+    t2, a2 = ops.roi_pool_forward(b2, r2, 7, 7, c["scale"])
+    wt2, wa2 = ref.roi_pool_fwd(b2, r2, 7, 7, c["scale"], threads=16)
+    assert np.array_equal(a2.cpu().numpy(), wa2) and np.array_equal(t2.cpu().numpy(), wt2)
+    g = np.random.default_rng(52).standard_normal(wt2.shape).astype(np.float32)
+    want_g = ref.roi_pool_bwd(g, wa2, r2, b2.shape, c["scale"], threads=16)
+    det = ops.roi_pool_backward(b2.shape, r2, a2, g, 7, 7, c["scale"], deterministic=True)
+    assert np.array_equal(det.cpu().numpy(), want_g)
+    atm = ops.roi_pool_backward(b2.shape, r2, a2, g, 7, 7, c["scale"], deterministic=False)
+    np.testing.assert_allclose(atm.cpu().numpy(), want_g, rtol=RTOL, atol=ATOL)
