@@ -31,6 +31,10 @@ comparison stays ``(double)ovr >= thresh`` exactly as in the reference.
                         defines Shard() as an even multi-threaded range split).  The kernels
                         are ALSO restated in ``oracle/hotpath_ref.c`` (faster, plus the CUDA
                         twin's bins); tests pin the restatement to this build.
+  ref_roi_pool_cudatwin.so <- code/lib/roi_pooling_layer/roi_pooling_op_gpu.cu.cc built FOR THE
+                        HOST (``oracle/tf_stub/cuda_emu.h``): the CUDA kernels' bodies (the
+                        GPU_CEIL bin arithmetic) run once per emulated thread; pins bin_mode
+                        GPU_CEIL of the restatement.
 
 Flags: ``-O2`` only; no ``-march=native``, no ``-ffast-math`` and
 ``-ffp-contract=off`` so that x86 FMA contraction can never change a result.
@@ -139,8 +143,53 @@ def build(force=False, verbose=False):
     return True
 
 
+CUDA_TWIN_SRC = "code/lib/roi_pooling_layer/roi_pooling_op_gpu.cu.cc"
+CUDA_TWIN_SO = os.path.join(OUT, "ref_roi_pool_cudatwin.so")
+
+
+def cuda_twin_built():
+    return os.path.isfile(CUDA_TWIN_SO)
+
+
+def build_cuda_twin(force=False, verbose=False):
+    """The reference's CUDA kernels (roi_pooling_op_gpu.cu.cc) compiled FOR THE HOST: g++ with
+    oracle/tf_stub/cuda_emu.h.  One build-time source edit: the two triple-chevron launch
+    statements become CUDA_EMU_LAUNCH(grid, block, kernel(args)) (a launch has no C++ spelling);
+    the kernel bodies -- the arithmetic -- are compiled as they are."""
+    if cuda_twin_built() and not force:
+        return True
+    src = os.path.join(REF, CUDA_TWIN_SRC)
+    if not os.path.isfile(src):
+        return False
+    os.makedirs(OUT, exist_ok=True)
+    text = open(src).read()
+    text, n = re.subn(r"(\w+)<<<(.*?),\s*(\w+),\s*0,\s*d\.stream\(\)>>>\((.*?)\);",
+                      r"CUDA_EMU_LAUNCH((\2), (\3), \1(\4));", text, flags=re.S)
+    if n != 2:
+        raise RuntimeError("expected 2 kernel launches in %s, found %d" % (CUDA_TWIN_SRC, n))
+    tmp = os.path.join(OUT, "ref_cuda_twin_tmp.cc")
+    with open(tmp, "w") as f:
+        f.write(text)
+    flags = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w",
+             "-DGOOGLE_CUDA=1", "-include", os.path.join(HERE, "tf_stub", "cuda_emu.h"),
+             "-I", os.path.join(HERE, "tf_stub"), "-I", os.path.dirname(src)]
+    try:
+        r = subprocess.run(["g++"] + flags + ["-shared", tmp,
+                                              os.path.join(HERE, "ref_roi_pool_cudatwin_driver.cc"),
+                                              "-o", CUDA_TWIN_SO], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed for the CUDA twin:\n%s\n%s" % (r.stdout, r.stderr))
+    finally:
+        os.remove(tmp)                   # no reference-derived source text stays in the tree
+    if verbose:
+        print("built", CUDA_TWIN_SO)
+    return True
+
+
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv, verbose=True)
     print("oracle/_ref:", "built" if ok else "reference not present; nothing built")
     ok = build_roi_pool(force="--force" in sys.argv, verbose=True)
     print("oracle/_ref/ref_roi_pool.so:", "built" if ok else "reference not present; not built")
+    ok = build_cuda_twin(force="--force" in sys.argv, verbose=True)
+    print("oracle/_ref/ref_roi_pool_cudatwin.so:", "built" if ok else "reference not present; not built")

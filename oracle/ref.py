@@ -127,3 +127,40 @@ def roi_pool_bwd(grad, argmax, rois, bottom_shape, spatial_scale, threads=1):
     if rc != 0:
         raise RuntimeError(err.value.decode())
     return out
+
+
+_twin_lib = None
+
+
+def cuda_twin_available():
+    """True when the reference's CUDA RoI-pool kernels have been built for the host
+    (oracle/build_ref.py:build_cuda_twin)."""
+    from . import build_ref
+    return build_ref.cuda_twin_built() or build_ref.build_cuda_twin()
+
+
+def roi_pool_fwd_cuda_twin(bottom, rois, pooled_h, pooled_w, spatial_scale):
+    """ROIPoolForwardLaucher / ROIPoolForward (roi_pooling_op_gpu.cu.cc:19-110), the kernel body
+    compiled for the host and called once per emulated CUDA thread: the GPU_CEIL bins."""
+    global _twin_lib
+    import ctypes
+    from . import build_ref
+    if _twin_lib is None:
+        if not cuda_twin_available():
+            raise ImportError("oracle/_ref/ref_roi_pool_cudatwin.so is not built and /root/reference is absent")
+        L = ctypes.CDLL(build_ref.CUDA_TWIN_SO)
+        vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        L.ref_roi_pool_fwd_cudatwin.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, cf, vp, vp]
+        _twin_lib = L
+    bottom = np.ascontiguousarray(bottom, np.float32)
+    rois = np.ascontiguousarray(rois, np.float32)
+    B, H, W, C = bottom.shape
+    R = rois.shape[0]
+    top = np.empty((R, pooled_h, pooled_w, C), np.float32)
+    arg = np.empty((R, pooled_h, pooled_w, C), np.int32)
+    rc = _twin_lib.ref_roi_pool_fwd_cudatwin(bottom.ctypes.data, rois.ctypes.data, H, W, C, R,
+                                             pooled_h, pooled_w, spatial_scale, top.ctypes.data,
+                                             arg.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("ROIPoolForwardLaucher failed")
+    return top, arg

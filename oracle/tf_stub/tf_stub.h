@@ -23,7 +23,10 @@
 
 namespace Eigen {
 struct ThreadPoolDevice {};
-struct GpuDevice {};
+struct GpuDevice {
+  void* stream() const { return nullptr; }
+  bool ok() const { return true; }
+};
 }  // namespace Eigen
 
 namespace tensorflow {

@@ -555,3 +555,28 @@ def test_reference_kernel_attribute_checks(oracle_mod):
     bottom = np.zeros((1, 4, 4, 2), np.float32)
     with pytest.raises(RuntimeError, match="pooled_height"):
         oracle_mod.ref.roi_pool_fwd(bottom, np.zeros((1, 5), np.float32), -1, 7, 1 / 16.)
+
+
+def test_gpu_ceil_restatement_equals_reference_cuda_kernel_source(oracle_mod):
+    """bin_mode GPU_CEIL of the C restatement versus the reference's CUDA kernel
+    (roi_pooling_op_gpu.cu.cc ROIPoolForward), whose body is compiled for the host and run once
+    per emulated CUDA thread (oracle/build_ref.py:build_cuda_twin, oracle/tf_stub/cuda_emu.h):
+    bit for bit, and different from the CPU op where the two bin rules differ."""
+    if not oracle_mod.ref.cuda_twin_available():
+        pytest.skip("oracle/_ref/ref_roi_pool_cudatwin.so not built (reference absent)")
+    clib, ref = oracle_mod.clib, oracle_mod.ref
+    differs = 0
+    for trial, (B, H, W, C) in enumerate([(2, 38, 50, 8), (3, 13, 17, 5), (1, 60, 61, 2)]):
+        bottom = syn.feature_map(96 + trial, B, H, W, C)
+        bottom[0, 1:3, 2:5] = -np.inf
+        bottom[B - 1, 0, 0, :] = np.nan
+        rois = np.concatenate([syn.rois_for_pool(97 + trial, 80, B, im_w=W * 16, im_h=H * 16),
+                               syn.adversarial_rois(B, W, H)])
+        for PH, PW in ((7, 7), (14, 14), (3, 5), (1, 1)):
+            top, arg = ref.roi_pool_fwd_cuda_twin(bottom, rois, PH, PW, 1 / 16.)
+            wt, wa = clib.roi_pool_fwd(bottom, rois, PH, PW, 1 / 16., bin_mode=clib.GPU_CEIL)
+            assert np.array_equal(arg, wa), (trial, PH, PW)
+            assert np.array_equal(top, wt, equal_nan=True), (trial, PH, PW)
+            _, ca = clib.roi_pool_fwd(bottom, rois, PH, PW, 1 / 16., bin_mode=clib.CPU_TRUNC)
+            differs += int(not np.array_equal(ca, wa))
+    assert differs >= 6          # the fork of SURVEY.md section 0.1 is real
