@@ -31,6 +31,8 @@ comparison stays ``(double)ovr >= thresh`` exactly as in the reference.
                         defines Shard() as an even multi-threaded range split).  The kernels
                         are ALSO restated in ``oracle/hotpath_ref.c`` (faster, plus the CUDA
                         twin's bins); tests pin the restatement to this build.
+  ref_gpu_nms_hostbuild.so <- code/lib/nms/nms_kernel.cu (devIoU, nms_kernel, _nms: the '>' NMS
+                        behind gpu_nms) built FOR THE HOST the same way (cuda_emu.h).
   ref_roi_pool_cudatwin.so <- code/lib/roi_pooling_layer/roi_pooling_op_gpu.cu.cc built FOR THE
                         HOST (``oracle/tf_stub/cuda_emu.h``): the CUDA kernels' bodies (the
                         GPU_CEIL bin arithmetic) run once per emulated thread; pins bin_mode
@@ -186,6 +188,48 @@ def build_cuda_twin(force=False, verbose=False):
     return True
 
 
+CUDA_NMS_SRC = "code/lib/nms/nms_kernel.cu"
+CUDA_NMS_SO = os.path.join(OUT, "ref_gpu_nms_hostbuild.so")
+
+
+def cuda_nms_built():
+    return os.path.isfile(CUDA_NMS_SO)
+
+
+def build_cuda_nms(force=False, verbose=False):
+    """The reference's CUDA NMS (nms/nms_kernel.cu: devIoU, nms_kernel, the host sweep _nms)
+    compiled FOR THE HOST with oracle/tf_stub/cuda_emu.h.  One build-time source edit: the
+    launch statement `nms_kernel<<<blocks, threads>>>(args);` becomes
+    CUDA_EMU_LAUNCH_SHARED(blocks, threads, nms_kernel(args));"""
+    if cuda_nms_built() and not force:
+        return True
+    src = os.path.join(REF, CUDA_NMS_SRC)
+    if not os.path.isfile(src):
+        return False
+    os.makedirs(OUT, exist_ok=True)
+    text = open(src).read()
+    text, n = re.subn(r"(\w+)<<<(\w+),\s*(\w+)>>>\((.*?)\);",
+                      r"CUDA_EMU_LAUNCH_SHARED(\2, \3, \1(\4));", text, flags=re.S)
+    if n != 1:
+        raise RuntimeError("expected 1 kernel launch in %s, found %d" % (CUDA_NMS_SRC, n))
+    tmp = os.path.join(OUT, "ref_cuda_nms_tmp.cc")
+    with open(tmp, "w") as f:
+        f.write(text)
+    flags = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w",
+             "-include", os.path.join(HERE, "tf_stub", "cuda_emu.h"), "-I", os.path.dirname(src)]
+    try:
+        r = subprocess.run(["g++"] + flags + ["-shared", tmp,
+                                              os.path.join(HERE, "ref_gpu_nms_driver.cc"),
+                                              "-o", CUDA_NMS_SO], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed for nms_kernel.cu:\n%s\n%s" % (r.stdout, r.stderr))
+    finally:
+        os.remove(tmp)
+    if verbose:
+        print("built", CUDA_NMS_SO)
+    return True
+
+
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv, verbose=True)
     print("oracle/_ref:", "built" if ok else "reference not present; nothing built")
@@ -193,3 +237,5 @@ if __name__ == "__main__":
     print("oracle/_ref/ref_roi_pool.so:", "built" if ok else "reference not present; not built")
     ok = build_cuda_twin(force="--force" in sys.argv, verbose=True)
     print("oracle/_ref/ref_roi_pool_cudatwin.so:", "built" if ok else "reference not present; not built")
+    ok = build_cuda_nms(force="--force" in sys.argv, verbose=True)
+    print("oracle/_ref/ref_gpu_nms_hostbuild.so:", "built" if ok else "reference not present; not built")

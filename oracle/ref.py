@@ -164,3 +164,40 @@ def roi_pool_fwd_cuda_twin(bottom, rois, pooled_h, pooled_w, spatial_scale):
     if rc != 0:
         raise RuntimeError("ROIPoolForwardLaucher failed")
     return top, arg
+
+
+_nms_lib = None
+
+
+def gpu_nms_available():
+    """True when nms/nms_kernel.cu has been built for the host (build_ref.build_cuda_nms)."""
+    from . import build_ref
+    return build_ref.cuda_nms_built() or build_ref.build_cuda_nms()
+
+
+def gpu_nms(dets, thresh):
+    """nms/gpu_nms.pyx:16-31 around the reference's own _nms (nms_kernel.cu:91-144, host build):
+    sort by score (:25-28), _nms on the sorted boxes, map the kept positions back (:31).
+    The '>' predicate in float32: `devIoU(...) > nms_overlap_thresh` (nms_kernel.cu:71)."""
+    global _nms_lib
+    import ctypes
+    from . import build_ref
+    if _nms_lib is None:
+        if not gpu_nms_available():
+            raise ImportError("oracle/_ref/ref_gpu_nms_hostbuild.so is not built and /root/reference is absent")
+        L = ctypes.CDLL(build_ref.CUDA_NMS_SO)
+        vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+        L.ref_gpu_nms_sorted.argtypes = [vp, vp, vp, ci, ci, cf]
+        L.ref_gpu_nms_sorted.restype = None
+        _nms_lib = L
+    dets = np.ascontiguousarray(dets, np.float32)
+    boxes_num, boxes_dim = dets.shape
+    if boxes_num == 0:
+        return []
+    keep = np.zeros(boxes_num, dtype=np.int32)
+    num_out = ctypes.c_int(0)
+    order = dets[:, 4].argsort()[::-1]
+    sorted_dets = np.ascontiguousarray(dets[order, :])
+    _nms_lib.ref_gpu_nms_sorted(keep.ctypes.data, ctypes.byref(num_out), sorted_dets.ctypes.data,
+                                boxes_num, boxes_dim, float(thresh))
+    return list(order[keep[:num_out.value]])

@@ -89,6 +89,12 @@ def test_modes_gt_and_contain(oracle_mod, golden):
             order = order[np.where(ovr <= np.float32(thresh))[0] + 1]
         return keep
     assert ops.nms(d, 0.5, ops.NMS_GT_F32) == py_nms(d, 0.5)
+    # the reference's own CUDA NMS (nms/nms_kernel.cu: devIoU, nms_kernel, _nms) built for the
+    # host (oracle/build_ref.py:build_cuda_nms) behind the gpu_nms.pyx glue
+    if oracle_mod.ref.gpu_nms_available():
+        assert ops.nms(d, 0.5, ops.NMS_GT_F32) == [int(k) for k in oracle_mod.ref.gpu_nms(d, 0.5)]
+        fork = golden["nms_fork_dets"]
+        assert [int(k) for k in oracle_mod.ref.gpu_nms(fork, 0.3)] == ops.nms(fork, 0.3, ops.NMS_GT_F32)
     for t in (0.3, 0.7):
         assert ops.nms(d, t, ops.NMS_GE_F64 | ops.NMS_CONTAIN) == oracle_mod.clib.nms(d, t, variant=1)
 

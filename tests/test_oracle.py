@@ -580,3 +580,28 @@ def test_gpu_ceil_restatement_equals_reference_cuda_kernel_source(oracle_mod):
             _, ca = clib.roi_pool_fwd(bottom, rois, PH, PW, 1 / 16., bin_mode=clib.CPU_TRUNC)
             differs += int(not np.array_equal(ca, wa))
     assert differs >= 6          # the fork of SURVEY.md section 0.1 is real
+
+
+def test_reference_cuda_nms_host_build_agrees_with_its_python_twin(oracle_mod, golden):
+    """nms/nms_kernel.cu (the '>' NMS behind gpu_nms: devIoU, the 64-bit bitmask kernel and the
+    host sweep _nms) built for the host (oracle/build_ref.py:build_cuda_nms) versus the
+    reference's pure-Python twin nms/py_cpu_nms.py loaded by path: same keep lists, and the
+    documented fork against cpu_nms ('>=' on a double threshold) at IoU == 0.3f / 0.7f."""
+    if not oracle_mod.ref.gpu_nms_available():
+        pytest.skip("oracle/_ref/ref_gpu_nms_hostbuild.so not built (reference absent)")
+    ref = oracle_mod.ref
+    fork = golden["nms_fork_dets"]
+    assert [int(k) for k in ref.gpu_nms(fork, 0.7)] == [0, 1, 2, 3]
+    assert [int(k) for k in ref.gpu_nms(fork, 0.3)] == [0, 2, 3]          # cpu_nms: [0, 2]
+    assert golden["nms_fork_keep_03"].tolist() == [0, 2]
+    if not REFERENCE_PRESENT:
+        return
+    spec = importlib.util.spec_from_file_location(
+        "ref_py_cpu_nms", "/root/reference/code/lib/nms/py_cpu_nms.py")
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    for seed, n, kw in ((300, 2500, {"clustered": True}), (301, 1000, {}), (302, 65, {}), (303, 64, {}),
+                        (304, 1, {}), (305, 129, {"clustered": True})):
+        d = syn.dets(seed, n, **kw)
+        for t in (0.3, 0.5, 0.7):
+            assert [int(k) for k in ref.gpu_nms(d, t)] == [int(k) for k in m.py_cpu_nms(d, t)]
