@@ -7,12 +7,16 @@
  * (wssdl_bus_b200/) never links, loads or calls it.
  *
  * Parity status
- *   roi_pool_*      : the reference's CPU kernels need TensorFlow 1.x headers
- *                     (roi_pooling_op.cc:21-26) and cannot be compiled here, and the
- *                     reference ships no golden vectors for them
- *                     (roi_pooling_op_test.py asserts nothing).  PARITY UNPINNED by
- *                     the reference's own tests; pinned only by this literal,
- *                     expression-for-expression restatement.
+ *   roi_pool_*      : PINNED.  bin_mode CPU_TRUNC is checked bit for bit (forward, backward,
+ *                     adversarial / malformed RoIs, arbitrary argmax tensors) against the
+ *                     reference's own RoiPool / RoiPoolGrad CPU kernels: roi_pooling_op.cc
+ *                     compiled UNMODIFIED against oracle/tf_stub (a stand-in for the TF op
+ *                     framework that holds no arithmetic) into oracle/_ref/ref_roi_pool.so.
+ *                     bin_mode GPU_CEIL is checked bit for bit against the reference's CUDA
+ *                     kernel source roi_pooling_op_gpu.cu.cc built for the host
+ *                     (oracle/_ref/ref_roi_pool_cudatwin.so).  Recipes: oracle/build_ref.py;
+ *                     tests: tests/test_oracle.py.  (The reference itself ships no golden
+ *                     vectors for the op: roi_pooling_op_test.py asserts nothing.)
  *   nms_ref, bbox_overlaps_ref, bbox_overlaps_ui_ref
  *                   : pinned -- checked bit-for-bit against the reference's own
  *                     Cython modules compiled into oracle/_ref (tests/test_oracle.py)
