@@ -121,3 +121,18 @@ def test_band_geometry_invariants():
         assert p["RB"] >= min(R, 16) and p["nchunks"] >= 1
         assert p["scan"] == (1 if R <= 4096 else 0)
     assert seen_multi > 20
+
+
+def test_generate_anchors_equals_the_reference_function_output(oracle_mod):
+    """Host generate_anchors (product) and the oracle restatement against what the reference's
+    own rpn_msr/generate_anchors.py returns when executed (tests/golden/make_layers_golden.py),
+    for the default, the 4-scale layer default and a non-standard base size / ratio set."""
+    import os
+    from wssdl_bus_b200.rpn_msr.generate_anchors import generate_anchors
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_layers_golden.npz"))
+    cases = (("anchors_default", {}),
+             ("anchors_4_8_16_32", dict(scales=np.array([4, 8, 16, 32]))),
+             ("anchors_ratios_1_2_base8", dict(base_size=8, ratios=[1, 2], scales=np.array([2, 16]))))
+    for key, kw in cases:
+        assert np.array_equal(generate_anchors(**kw), g[key]), key
+        assert np.array_equal(oracle_mod.layers.generate_anchors(**kw), g[key]), key
