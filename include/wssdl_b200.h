@@ -41,6 +41,29 @@ enum {
 int wssdl_version(void);                    /* 100 * major + minor */
 const char* wssdl_error_string(int code);   /* static string, also for cudaError_t codes */
 
+/* Process-wide tuning switches, for experiments and for tests that must reach one particular
+ * kernel.  Their defaults are read from the environment ONCE, at the first call into the
+ * library (the variable named beside each key); no entry point reads the environment per
+ * launch.  Results never depend on them: every kernel variant produces the same bytes.
+ * wssdl_set_tuning returns WSSDL_OK or WSSDL_EINVAL (unknown key). */
+enum {
+  WSSDL_TUNE_ROI_FWD_KERNEL = 0,    /* 0 by shape, 1 direct, 2 tiled, 3 band, 4 sorted bins
+                                       (WSSDL_ROI_FWD_KERNEL=direct|tiled|band|sorted)          */
+  WSSDL_TUNE_ROI_FWD_SLICES = 1,    /* sorted bins: 32-channel slices per CTA, 0 = by shape
+                                       (WSSDL_ROI_FWD_SLICES)                                    */
+  WSSDL_TUNE_ROI_FWD_CHUNKS = 2,    /* sorted bins: RoI chunks per image, 0 = by shape
+                                       (WSSDL_ROI_FWD_CHUNKS)                                    */
+  WSSDL_TUNE_NMS_SWEEP_CLUSTER = 3, /* -1 by size, 0 single-CTA sweep, 1 cluster sweep
+                                       (WSSDL_NMS_SWEEP_CLUSTER)                                 */
+  WSSDL_TUNE_PROPOSALS_CLUSTER = 4, /* -1 by shape, 0 one CTA per image, 1 cluster per image
+                                       (WSSDL_PROPOSALS_CLUSTER)                                 */
+  WSSDL_TUNE_ROI_FWD_THREADS = 5,   /* sorted bins: threads per pooling CTA, 0 = default,
+                                       1024 (one CTA per SM) or 512 (two)  (WSSDL_ROI_FWD_THREADS) */
+  WSSDL_TUNE_COUNT = 6
+};
+int wssdl_set_tuning(int key, int value);
+int wssdl_get_tuning(int key);
+
 /* ---------------------------------------------------------------- RoI max pooling
  * Replaces ROIPoolForwardLaucher / ROIPoolBackwardLaucher
  * (roi_pooling_layer/roi_pooling_op_gpu.h:18-27) and the CPU op bodies
@@ -56,27 +79,33 @@ const char* wssdl_error_string(int code);   /* static string, also for cudaError
  * A RoI whose batch index is outside [0,B) yields top=0/argmax=-1 (the reference reads
  * out of bounds).  16-byte aligned pointers and C%4==0 select the vectorised kernels;
  * anything else runs the scalar variant of the direct kernel.
- * workspace   optional scratch of wssdl_roi_pool_fwd_workspace_bytes(B, R) bytes (device,
- *             4-byte aligned; may be NULL).  With it, batches of more than 4096 RoIs can
- *             use the shared-memory-resident kernels (RoIs are counting-sorted by image into
- *             the workspace first, two small kernels on the same stream); without it they
- *             run the direct kernel.  Results are identical either way.
- * Three kernels give the same bytes and are picked by shape (csrc/roi_pool.cu): "band"
- * (32-channel slice of overlapping row bands of the map in shared memory; the detector's
- * 7x7 shapes), "direct" (one CTA per output row reading L2; big bins, awkward grid sizes),
- * "tiled" (16-channel slice of the whole map; C % 32 != 0).  The environment variable
- * WSSDL_ROI_FWD_KERNEL=band|direct|tiled forces one where the shape allows (experiments).
+ * workspace   optional scratch of wssdl_roi_pool_fwd_workspace_bytes(B, R, PH, PW) bytes
+ *             (device, 16-byte aligned; may be NULL).  It holds the RoIs grouped by image
+ *             (batches of more than 4096 RoIs: two small kernels on the same stream) and the
+ *             sorted-bins kernel's class-sorted bin records (8 bytes per output bin, written
+ *             by its sort pre-pass on the same stream).  Without it small batches run the
+ *             band / tiled kernel and big ones the direct kernel.  Results are identical
+ *             either way.
+ * Four kernels give the same bytes and are picked by shape (csrc/roi_pool.cu,
+ * csrc/roi_pool_bins.cu): "sorted" (32-channel slice of overlapping row bands of the map
+ * staged in shared memory by one TMA tensor copy; the bins a CTA owns are counting-sorted by
+ * size class so that every warp runs uniform loops; the detector's 7x7 shapes), "direct" (one
+ * CTA per output row reading L2; big bins), "tiled" (16-channel slice of the whole map;
+ * C % 32 != 0), "band" (the sorted kernel's predecessor: same staging, one thread per column
+ * of bins; kept as the cross-check).  WSSDL_TUNE_ROI_FWD_KERNEL forces one where the shape
+ * allows.
  */
 enum { WSSDL_BIN_CPU_TRUNC = 0, WSSDL_BIN_GPU_CEIL = 1 };
 
-size_t wssdl_roi_pool_fwd_workspace_bytes(int B, int R);
+size_t wssdl_roi_pool_fwd_workspace_bytes(int B, int R, int PH, int PW);
 
 /* Host-only query (no CUDA call): which forward kernel a call of this shape takes and its
  * launch geometry, for tests and tuning.  force: 0 = by shape, 1 = direct, 2 = tiled,
- * 3 = band.  out[8] = { kernel (0 direct, 1 tiled, 2 band), row bands per image, rows per
- * band, first-row distance of two bands, RoI chunks per image, RoIs whose bin edges are
- * resident at a time, dynamic shared memory bytes, 1 if the RoI lists are built in-kernel }.
- * Assumes aligned pointers. */
+ * 3 = band, 4 = sorted bins.  out[8] = { kernel (0 direct, 1 tiled, 2 band, 3 sorted bins),
+ * row bands per image, rows per band, first-row distance of two bands, RoI chunks per image,
+ * RoIs whose bin edges are resident at a time, dynamic shared memory bytes, 1 if the RoI
+ * lists are built in-kernel }; sorted bins also fills out[8] = 32-channel slices per CTA and
+ * out[9] = bin records resident at a time.  `out` holds 10 ints.  Assumes aligned pointers. */
 int wssdl_roi_pool_fwd_plan(int B, int H, int W, int C, int R, int PH, int PW,
                             int with_workspace, int force, int* out);
 

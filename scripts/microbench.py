@@ -13,7 +13,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from wssdl_bus_b200 import ops, synthetic as syn  # noqa: E402
+from wssdl_bus_b200 import _lib, ops, synthetic as syn  # noqa: E402
 from wssdl_bus_b200.pipeline import HotPath  # noqa: E402
 
 PEAK = 6553.0
@@ -93,6 +93,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--only", default="")
+    ap.add_argument("--kernels", default="", help="roicmp: comma list of forward kernels")
     ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle (1 core)")
     args = ap.parse_args()
     out = open(args.out, "a") if args.out else None
@@ -101,29 +102,26 @@ def main():
     def want(name):
         return (only is None and name not in ("roi4", "roicmp")) or (only is not None and name in only)
 
-    emit(out, op="env", gpu=torch.cuda.get_device_name(0), peak_gbs=PEAK,
-         vpt=os.environ.get("WSSDL_ROI_FWD_VPT", "default"), occ=os.environ.get("WSSDL_ROI_FWD_OCC", "default"))
+    emit(out, op="env", gpu=torch.cuda.get_device_name(0), peak_gbs=PEAK)
     if want("roi4"):
         r256 = realistic_rois(256)
         bench_roi(out, "C4 256 images x 300 proposal RoIs", 256, 512, 7, 7, r256, bwd=False)
     if want("roicmp"):
-        # direct vs tiled forward kernel on every BASELINE shape (env knobs are read per call)
+        # every forward kernel on every BASELINE shape
         r1 = realistic_rois(1)
         r256 = realistic_rois(256)
         ru = torch.from_numpy(syn.rois_for_pool(5, 16 * 300, 16)).cuda()
         ru = ru[torch.argsort(ru[:, 0], stable=True)].contiguous()
-        for kern, st in (("direct", "1"), ("tiled", "1"), ("band", "1")):
-            os.environ["WSSDL_ROI_FWD_KERNEL"] = kern
-            os.environ["WSSDL_ROI_FWD_STREAM_ST"] = st
-            tag = "[%s st=%s] " % (kern, st)
+        for kern in (args.kernels.split(",") if args.kernels else ("direct", "tiled", "band", "sorted")):
+            _lib.set_tuning("roi_fwd_kernel", kern)
+            tag = "[%s] " % kern
             bench_roi(out, tag + "C4 256x300", 256, 512, 7, 7, r256, bwd=False)
             bench_roi(out, tag + "C4 256x300 GPU_CEIL", 256, 512, 7, 7, r256, mode="gpu", bwd=False)
             bench_roi(out, tag + "C1 1x300", 1, 512, 7, 7, r1, bwd=False)
             bench_roi(out, tag + "C2 1x128", 1, 512, 7, 7, r1[:128].contiguous(), bwd=False)
             bench_roi(out, tag + "16x300 7x7 C512", 16, 512, 7, 7, realistic_rois(16), bwd=False)
             bench_roi(out, tag + "C3 16x1024 4800 RoIs 14x14", 16, 1024, 14, 14, ru, bwd=False)
-        os.environ.pop("WSSDL_ROI_FWD_KERNEL")
-        os.environ.pop("WSSDL_ROI_FWD_STREAM_ST")
+        _lib.set_tuning("roi_fwd_kernel", "auto")
     if want("roi"):
         r1 = realistic_rois(1)
         bench_roi(out, "C1 single image (300 proposal RoIs)", 1, 512, 7, 7, r1)

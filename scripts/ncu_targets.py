@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small driver for ncu captures of the secondary kernels (one shape each, few launches):
-   python scripts/ncu_targets.py nms|iou|detect|bwd"""
+   python scripts/ncu_targets.py nms|iou|detect|bwd|roi4[:kernel[:slices[:chunks[:threads]]]]"""
 import os
 import sys
 
@@ -37,4 +37,24 @@ elif what == "bwd":
     g = torch.randn_like(top)
     for _ in range(3):
         ops.roi_pool_backward((B, H, W, C), r, arg, g, 14, 14, 1 / 16.)
+elif what.startswith("roi4"):
+    # the C4 RoI-pool forward launch (256 images x 300 proposal RoIs), 3 launches
+    from wssdl_bus_b200 import _lib
+    from wssdl_bus_b200.pipeline import HotPath
+    parts = what.split(":")
+    nimg = 256
+    cls, reg, info = syn.rpn_outputs(0, nimg, 38, 50, 9)
+    hot = HotPath()
+    rois = ops.proposals(cls, reg, info, hot.base, 16, hot.pre, hot.post, hot.thresh, hot.min_size)["rois"]
+    x = torch.from_numpy(syn.feature_map(1, nimg, 38, 50, 512)).cuda()
+    if len(parts) > 1:
+        _lib.set_tuning("roi_fwd_kernel", parts[1])
+    if len(parts) > 2:
+        _lib.set_tuning("roi_fwd_slices", int(parts[2]))
+    if len(parts) > 3:
+        _lib.set_tuning("roi_fwd_chunks", int(parts[3]))
+    if len(parts) > 4:
+        _lib.set_tuning("roi_fwd_threads", int(parts[4]))
+    for _ in range(3):
+        ops.roi_pool_forward(x, rois, 7, 7, 1 / 16.)
 torch.cuda.synchronize()

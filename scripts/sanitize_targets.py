@@ -9,41 +9,41 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from wssdl_bus_b200 import ops, synthetic as syn  # noqa: E402
+from wssdl_bus_b200 import _lib, ops, synthetic as syn  # noqa: E402
 from wssdl_bus_b200.rpn_msr.generate_anchors import generate_anchors  # noqa: E402
 
 B, H, W, C = 2, 38, 50, 32
 feat = torch.from_numpy(syn.feature_map(0, B, H, W, C)).cuda()
 rois = np.concatenate([syn.rois_for_pool(1, 90, B), syn.adversarial_rois(B, W, H)])
-for kern in ("direct", "tiled", "band"):
-    os.environ["WSSDL_ROI_FWD_KERNEL"] = kern
+for kern in ("direct", "tiled", "band", "sorted"):
+    _lib.set_tuning("roi_fwd_kernel", kern)
     for mode in ("cpu", "gpu"):
         top, arg = ops.roi_pool_forward(feat, rois, 7, 7, 1 / 16., bin_mode=mode)
-# band kernel, linear-index variant (C % 128 == 0) incl. bins taller than the band overlap
+# sorted-bins kernel, linear-index variant (C % 128 == 0) incl. bins taller than the band overlap
 feat128 = torch.from_numpy(syn.feature_map(9, B, H, W, 128)).cuda()
 tall = np.array([[0, 100, -900, 500, 1700], [1, 0, 0, 799, 599]], np.float32)
 ops.roi_pool_forward(feat128, np.concatenate([rois, tall]), 7, 7, 1 / 16.)
 # counting-sort pre-pass (R > 4096): histogram + scatter kernels, then tiled / band
 big = syn.rois_for_pool(2, 4200, B)
-for kern in ("tiled", "band"):
-    os.environ["WSSDL_ROI_FWD_KERNEL"] = kern
+for kern in ("tiled", "band", "sorted"):
+    _lib.set_tuning("roi_fwd_kernel", kern)
     top2, arg2 = ops.roi_pool_forward(feat, big, 7, 7, 1 / 16.)
-os.environ.pop("WSSDL_ROI_FWD_KERNEL")
+_lib.set_tuning("roi_fwd_kernel", "auto")
 g = torch.randn_like(top)
 for det in (False, True):
     ops.roi_pool_backward((B, H, W, C), rois, arg, g, 7, 7, 1 / 16., deterministic=det)
 cls, reg, info = syn.rpn_outputs(3, B, H, W, 9)
-for cl in ("0", "1"):     # one CTA per image / cluster of 8 CTAs per image
-    os.environ["WSSDL_PROPOSALS_CLUSTER"] = cl
+for cl in (0, 1):     # one CTA per image / cluster of 8 CTAs per image
+    _lib.set_tuning("proposals_cluster", cl)
     ops.proposals(cls, reg, info, generate_anchors(), 16, 6000, 300, 0.7, 16)
     ops.proposals(cls, reg, info, generate_anchors(), 16, 2000, 500, 0.7, 16, want_decoded=True)
-os.environ.pop("WSSDL_PROPOSALS_CLUSTER")
+_lib.set_tuning("proposals_cluster", -1)
 d = syn.dets(4, 5000)
-for cl in ("0", "1"):     # single-CTA sweep / cluster sweep
-    os.environ["WSSDL_NMS_SWEEP_CLUSTER"] = cl
+for cl in (0, 1):     # single-CTA sweep / cluster sweep
+    _lib.set_tuning("nms_sweep_cluster", cl)
     ops.nms(d, 0.7)
     ops.nms(d, 0.3, mode=ops.NMS_GT_F32 | ops.NMS_CONTAIN)
-os.environ.pop("WSSDL_NMS_SWEEP_CLUSTER")
+_lib.set_tuning("nms_sweep_cluster", -1)
 b = syn.random_boxes(5, 3000).astype(np.float64)
 q = syn.random_boxes(6, 130).astype(np.float64)
 ops.bbox_overlaps(b, q)

@@ -39,3 +39,18 @@ def oracle_mod():
     import oracle
     oracle.clib.build()
     return oracle
+
+
+@pytest.fixture
+def tuning():
+    """tuning(key, value): sets a process-wide tuning switch of libwssdl_b200.so through the C
+    ABI (wssdl_set_tuning) for the duration of the test."""
+    from wssdl_bus_b200 import _lib
+    saved = []
+
+    def set_(key, value):
+        saved.append((key, _lib.set_tuning(key, value)))
+
+    yield set_
+    for key, prev in reversed(saved):
+        _lib.set_tuning(key, prev)

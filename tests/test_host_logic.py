@@ -58,40 +58,88 @@ def test_numa_binding_is_a_noop_without_a_visible_topology():
 
 # ---------------------------------------------------------------- RoI-pool forward dispatch
 # wssdl_roi_pool_fwd_plan is a host-only query (no CUDA call): the kernel a shape takes and the
-# row-band geometry of the band kernel (csrc/roi_pool.cu: choose_fwd / plan_band).
-DIRECT, TILED, BAND = 0, 1, 2
+# row-band geometry of the band / sorted-bins kernels (csrc/roi_pool.cu: choose_fwd / plan_band,
+# csrc/roi_pool_bins.cu: plan_bins).
+DIRECT, TILED, BAND, SORTED = 0, 1, 2, 3
 
 
 def _plan(B, H, W, C, R, PH, PW, ws=True, force=0):
     import ctypes
     from wssdl_bus_b200 import _lib
-    out = (ctypes.c_int * 8)()
+    out = (ctypes.c_int * 10)()
     rc = _lib.lib().wssdl_roi_pool_fwd_plan(B, H, W, C, R, PH, PW, int(ws), force, out)
     assert rc == 0
-    return dict(zip(("kernel", "NB", "Hb", "step", "nchunks", "RB", "smem", "scan"), list(out)))
+    return dict(zip(("kernel", "NB", "Hb", "step", "nchunks", "RB", "smem", "scan", "slices",
+                     "threads"), list(out)))
 
 
 def test_fwd_kernel_choice_on_the_baseline_shapes():
-    # C4 (the bench workload): band kernel, two bands of 23 rows, RoI lists from the workspace
+    # C4 (the bench workload): sorted-bins kernel, two bands of 23 rows, RoI lists from the
+    # workspace
     p = _plan(256, 38, 50, 512, 256 * 300, 7, 7)
-    assert (p["kernel"], p["NB"], p["Hb"], p["step"], p["scan"]) == (BAND, 2, 23, 15, 0)
-    # C1 / C2 (one image): band kernel, lists built in-kernel, RoIs split so the grid is one wave
+    assert (p["kernel"], p["NB"], p["Hb"], p["step"], p["scan"]) == (SORTED, 2, 23, 15, 0)
+    # C1 / C2 (one image): sorted bins, lists built in-kernel, RoIs split so the grid is one wave
     for R in (300, 128):
         p = _plan(1, 38, 50, 512, R, 7, 7)
-        assert p["kernel"] == BAND and p["scan"] == 1
-        assert (512 // 32) * p["NB"] * p["nchunks"] <= 148
-    # C3 (14x14 bins on 1024 channels) and a grid of a few ragged waves: direct kernel
+        assert p["kernel"] == SORTED and p["scan"] == 1
+        assert -(-(512 // 32) // p["slices"]) * p["NB"] * p["nchunks"] <= 148
+    # 16 / 32 images (the per-rank batches of the strong-scaling run): sorted bins as well
+    assert _plan(16, 38, 50, 512, 16 * 300, 7, 7)["kernel"] == SORTED
+    assert _plan(32, 38, 50, 512, 32 * 300, 7, 7)["kernel"] == SORTED
+    # C3 (14x14 bins on 1024 channels): direct kernel
     assert _plan(16, 38, 50, 1024, 4800, 14, 14)["kernel"] == DIRECT
-    assert _plan(16, 38, 50, 512, 16 * 300, 7, 7)["kernel"] == DIRECT
     # C % 32 != 0: the 16-channel tiled kernel takes single images; C % 16 != 0: direct
     assert _plan(1, 38, 50, 48, 300, 7, 7)["kernel"] == TILED
     assert _plan(1, 38, 50, 20, 300, 7, 7)["kernel"] == DIRECT
-    # > 4096 RoIs without a workspace: nothing to group them with
+    # without a workspace: no room for the bin records (band kernel while the lists can be
+    # built in-kernel), > 4096 RoIs: nothing to group them with either
+    assert _plan(1, 38, 50, 512, 300, 7, 7, ws=False)["kernel"] in (DIRECT, TILED)
+    assert _plan(1, 38, 50, 512, 300, 7, 7, ws=False, force=3)["kernel"] == BAND
     assert _plan(256, 38, 50, 512, 256 * 300, 7, 7, ws=False)["kernel"] == DIRECT
     # forcing
     assert _plan(256, 38, 50, 512, 256 * 300, 7, 7, force=1)["kernel"] == DIRECT
     assert _plan(256, 38, 50, 512, 256 * 300, 7, 7, force=2)["kernel"] == TILED
+    assert _plan(256, 38, 50, 512, 256 * 300, 7, 7, force=3)["kernel"] == BAND
     assert _plan(16, 38, 50, 1024, 4800, 14, 14, force=3)["kernel"] == BAND
+    assert _plan(16, 38, 50, 1024, 4800, 7, 7, force=4)["kernel"] == SORTED
+
+
+def test_sorted_bins_plan_invariants():
+    """Seeded sweep of shapes: whenever the sorted-bins kernel is available its bands cover the
+    map and overlap by at least the tallest bin of a RoI inside the map, a band's cells fit the
+    11-bit first-cell field of a bin record, and the band fits the shared memory of a CTA (one or
+    two CTAs per SM)."""
+    from wssdl_bus_b200 import _lib
+    rng = np.random.default_rng(11)
+    seen = seen_multi = 0
+    try:
+        for threads in (0, 512):
+            _lib.set_tuning("roi_fwd_threads", threads)
+            for _ in range(400):
+                B = int(rng.integers(1, 40))
+                H, W = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+                C = int(rng.choice([32, 64, 128, 256, 512, 1024]))
+                R = int(rng.choice([1, 17, 300, 4096, 4097, 20000]))
+                PH, PW = int(rng.integers(1, 10)), int(rng.integers(1, 10))
+                p = _plan(B, H, W, C, R, PH, PW, force=4)
+                if p["kernel"] != SORTED:
+                    continue
+                seen += 1
+                NB, Hb, step = p["NB"], p["Hb"], p["step"]
+                assert 1 <= NB <= 4 and step >= 1 and 1 <= Hb <= H
+                assert (NB - 1) * step + Hb >= H
+                assert Hb * W <= 2047 and PH * PW <= 64
+                if NB > 1:
+                    seen_multi += 1
+                    assert Hb - step >= -(-(H + 1) // PH) + 2
+                assert p["threads"] == (512 if threads == 512 else 1024)
+                assert 1 <= p["RB"] <= 1024 and p["nchunks"] >= 1 and 1 <= p["slices"] <= C // 32
+                cap = 113 * 1024 if threads == 512 else 227 * 1024 - 1024
+                assert Hb * W * 128 + 128 <= p["smem"] <= cap
+                assert p["scan"] == (1 if R <= 4096 else 0)
+    finally:
+        _lib.set_tuning("roi_fwd_threads", 0)
+    assert seen > 100 and seen_multi > 10
 
 
 def test_band_geometry_invariants():

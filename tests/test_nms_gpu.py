@@ -10,10 +10,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(autouse=True, params=["cta", "cluster"])
-def sweep_variant(request, monkeypatch):
+def sweep_variant(request, tuning):
     """Every test runs twice: the single-CTA sweep and the sweep over a thread-block cluster
     of 8 CTAs (csrc/nms.cu; the default picks the cluster from N = 65536)."""
-    monkeypatch.setenv("WSSDL_NMS_SWEEP_CLUSTER", "1" if request.param == "cluster" else "0")
+    tuning("nms_sweep_cluster", 1 if request.param == "cluster" else 0)
     return request.param
 
 

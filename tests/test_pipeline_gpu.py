@@ -48,7 +48,7 @@ def test_host_pipeline_equals_device_path():
     assert hp.h2d_bytes == sum(x.nbytes for x in (feat, cls, reg, info))
 
 
-def test_c4_full_batch_properties_and_kernel_agreement(oracle_mod, monkeypatch):
+def test_c4_full_batch_properties_and_kernel_agreement(oracle_mod, tuning):
     """BASELINE config C4 at full size (256 images x 300 RoIs, 38x50x512, 7x7 = the bench.py
     step): the oracle checks a sample of images end to end; the whole batch is checked through
     size-independent properties (every image keeps 300 RoIs in descending-score order, RoIs are
@@ -58,7 +58,7 @@ def test_c4_full_batch_properties_and_kernel_agreement(oracle_mod, monkeypatch):
     feat, cls, reg, info = _inputs(7000, B)
     x = torch.from_numpy(feat).cuda()
     hot = HotPath()
-    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", "direct")
+    tuning("roi_fwd_kernel", "direct")
     p = hot.run(x, cls, reg, info)
     boxes, scores, cnt = hot.detections(p)
     assert cnt.cpu().numpy().tolist() == [300] * B
@@ -88,8 +88,8 @@ def test_c4_full_batch_properties_and_kernel_agreement(oracle_mod, monkeypatch):
         assert np.array_equal(top[b * 300:(b + 1) * 300].cpu().numpy(), wt)
         assert np.array_equal(arg[b * 300:(b + 1) * 300].cpu().numpy(), wa)
     # the shared-memory kernel (counting-sort pre-pass, workspace) gives the same bytes
-    for kern in ("tiled", "band"):
-        monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
+    for kern in ("tiled", "band", "sorted"):
+        tuning("roi_fwd_kernel", kern)
         top2, arg2 = ops.roi_pool_forward(x, r, 7, 7, 1 / 16.)
         assert torch.equal(top2, top) and torch.equal(arg2, arg), kern
         del top2, arg2

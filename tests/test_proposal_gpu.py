@@ -16,11 +16,11 @@ RTOL = 1e-5
 
 
 @pytest.fixture(autouse=True, params=["cta", "cluster"])
-def proposals_variant(request, monkeypatch):
+def proposals_variant(request, tuning):
     """Every test runs twice: one CTA per image, and a thread-block cluster of 8 CTAs per
     image (csrc/proposal.cu: the keep-list NMS is split over the cluster and its partial
     bitmaps are exchanged through distributed shared memory).  The default picks by batch size."""
-    monkeypatch.setenv("WSSDL_PROPOSALS_CLUSTER", "1" if request.param == "cluster" else "0")
+    tuning("proposals_cluster", 1 if request.param == "cluster" else 0)
     return request.param
 
 

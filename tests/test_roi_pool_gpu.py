@@ -13,14 +13,16 @@ pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-5
 
 
-@pytest.fixture(params=["direct", "tiled", "band"])
-def fwd_kernel(request, monkeypatch):
-    """Forces one of the three forward kernels (roi_pool.cu: direct = one CTA per output row
+@pytest.fixture(params=["direct", "tiled", "band", "sorted"])
+def fwd_kernel(request, tuning):
+    """Forces one of the four forward kernels (roi_pool.cu: direct = one CTA per output row
     reading L2; tiled = shared-memory resident 16-channel slice of the whole map; band =
-    32-channel slice of overlapping row bands; C % 128 == 0 takes its linear-index variant).
+    32-channel slice of overlapping row bands, one thread per column of bins; roi_pool_bins.cu:
+    sorted = same staging by TMA, bins counting-sorted by size class; C % 128 == 0 takes the
+    linear-index variant of band / sorted).
     Shapes a shared-memory kernel does not take (C % 16 / 32 != 0, misaligned pointers) fall
     through to the direct one."""
-    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", request.param)
+    tuning("roi_fwd_kernel", request.param)
     return request.param
 
 
@@ -76,12 +78,12 @@ def test_fwd_misaligned_pointer_uses_scalar_kernel(oracle_mod):
     assert np.array_equal(top.cpu().numpy(), wt) and np.array_equal(arg.cpu().numpy(), wa)
 
 
-@pytest.mark.parametrize("kern,C", [("tiled", 32), ("band", 32), ("band", 128)])
+@pytest.mark.parametrize("kern,C", [("tiled", 32), ("band", 32), ("band", 128), ("sorted", 32), ("sorted", 128)])
 @pytest.mark.parametrize("mode", ["cpu", "gpu"])
-def test_fwd_tiled_sorted_lists_many_images(oracle_mod, mode, kern, C, monkeypatch):
+def test_fwd_tiled_sorted_lists_many_images(oracle_mod, mode, kern, C, tuning):
     """R > 4096: the shared-memory kernels take their per-image RoI lists from the counting-sort
     pre-pass in the workspace.  Batch indices are shuffled and some are out of range."""
-    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
+    tuning("roi_fwd_kernel", kern)
     B, H, W = 24, 38, 50
     bottom = syn.feature_map(30, B, H, W, C)
     rois = np.concatenate([syn.rois_for_pool(31, 5000, B), syn.adversarial_rois(B, W, H)])
@@ -98,17 +100,17 @@ def test_fwd_tiled_sorted_lists_many_images(oracle_mod, mode, kern, C, monkeypat
     assert np.array_equal(a[~bad], wa[~bad]) and np.array_equal(t[~bad], wt[~bad])
     assert not t[bad].any() and (a[bad] == -1).all()
     # same answer from the direct kernel and without a workspace
-    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", "direct")
+    tuning("roi_fwd_kernel", "direct")
     t2, a2 = ops.roi_pool_forward(bottom, rois, 7, 7, 1 / 16., bin_mode=mode)
     assert np.array_equal(t2.cpu().numpy(), t) and np.array_equal(a2.cpu().numpy(), a)
 
 
-@pytest.mark.parametrize("kern,C", [("tiled", 48), ("band", 64), ("band", 128)])
+@pytest.mark.parametrize("kern,C", [("tiled", 48), ("band", 64), ("band", 128), ("sorted", 64), ("sorted", 128)])
 @pytest.mark.parametrize("B,R", [(1, 300), (2, 700), (3, 40), (5, 4096), (1, 1)])
-def test_fwd_tiled_chunked_scan_lists(oracle_mod, B, R, kern, C, monkeypatch):
+def test_fwd_tiled_chunked_scan_lists(oracle_mod, B, R, kern, C, tuning):
     """R <= 4096: RoI lists are built inside each CTA; few images split their RoIs over
     several CTAs (chunk = RoI index mod nchunks).  Also without argmax."""
-    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
+    tuning("roi_fwd_kernel", kern)
     H, W = 38, 50
     bottom = syn.feature_map(33, B, H, W, C)
     rois = syn.rois_for_pool(34, R, B)
@@ -124,7 +126,7 @@ def test_fwd_workspace_query_and_null_workspace(oracle_mod):
     import ctypes
     from wssdl_bus_b200 import _lib
     L = _lib.lib()
-    assert L.wssdl_roi_pool_fwd_workspace_bytes(256, 76800) >= 4 * (256 + 2 + 76800)
+    assert L.wssdl_roi_pool_fwd_workspace_bytes(256, 76800, 7, 7) >= 4 * (256 + 2 + 76800) + 8 * 76800 * 49
     B, H, W, C, R = 4, 20, 24, 16, 5000
     bottom = syn.feature_map(35, B, H, W, C)
     rois = syn.rois_for_pool(36, R, B, im_w=W * 16, im_h=H * 16)
@@ -235,14 +237,14 @@ def test_c3_resnet_shapes_properties(oracle_mod):
     np.testing.assert_allclose(gb.cpu().numpy(), gd.cpu().numpy(), rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize("kern,C", [("band", 96), ("band", 128)])
+@pytest.mark.parametrize("kern,C", [("band", 96), ("band", 128), ("sorted", 96), ("sorted", 128)])
 @pytest.mark.parametrize("mode", ["cpu", "gpu"])
-def test_fwd_band_bins_taller_than_the_overlap(oracle_mod, mode, kern, C, monkeypatch):
+def test_fwd_band_bins_taller_than_the_overlap(oracle_mod, mode, kern, C, tuning):
     """Band kernel: a 38x50 map is held as two overlapping row bands.  RoIs several times
     taller than the map have bins that no band holds completely: those take the kernel's
     global-memory path.  Mixed with ordinary RoIs, RoIs whose bins all belong to one band,
     and RoIs that start far above / end far below the map."""
-    monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
+    tuning("roi_fwd_kernel", kern)
     B, H, W = 3, 38, 50
     bottom = syn.feature_map(40, B, H, W, C)
     rng = np.random.default_rng(41)
@@ -260,7 +262,7 @@ def test_fwd_band_bins_taller_than_the_overlap(oracle_mod, mode, kern, C, monkey
         assert np.array_equal(a, wa) and np.array_equal(t, wt), (PH, PW)
 
 
-def test_fwd_random_shape_sweep_both_kernels(oracle_mod, monkeypatch):
+def test_fwd_random_shape_sweep_both_kernels(oracle_mod, tuning):
     """Seeded sweep over map sizes, channel counts, pooled sizes, scales and RoI counts (incl.
     PH != PW, maps that barely fit / do not fit the shared-memory slice, C = 16, single RoIs):
     direct, tiled and band kernels against the oracle, both bin modes."""
@@ -279,8 +281,8 @@ def test_fwd_random_shape_sweep_both_kernels(oracle_mod, monkeypatch):
         mode = "cpu" if trial % 2 == 0 else "gpu"
         want_top, want_arg = oracle_mod.clib.roi_pool_fwd(bottom, rois, PH, PW, 1.0 / stride,
                                                           bin_mode=0 if mode == "cpu" else 1)
-        for kern in ("direct", "tiled", "band"):
-            monkeypatch.setenv("WSSDL_ROI_FWD_KERNEL", kern)
+        for kern in ("direct", "tiled", "band", "sorted"):
+            tuning("roi_fwd_kernel", kern)
             top, arg = ops.roi_pool_forward(bottom, rois, PH, PW, 1.0 / stride, bin_mode=mode)
             ctx = (trial, kern, B, H, W, C, PH, PW, stride, R, mode)
             assert np.array_equal(arg.cpu().numpy(), want_arg), ctx

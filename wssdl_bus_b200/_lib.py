@@ -24,7 +24,9 @@ _vp, _i, _f, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_d
 SIGNATURES = {
     "wssdl_version": (_i, []),
     "wssdl_error_string": (ctypes.c_char_p, [_i]),
-    "wssdl_roi_pool_fwd_workspace_bytes": (_sz, [_i, _i]),
+    "wssdl_set_tuning": (_i, [_i, _i]),
+    "wssdl_get_tuning": (_i, [_i]),
+    "wssdl_roi_pool_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "wssdl_roi_pool_fwd_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "wssdl_roi_pool_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _sz,
                                 _vp]),
@@ -89,6 +91,23 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+# wssdl_set_tuning keys / values (include/wssdl_b200.h)
+TUNE_KEYS = {"roi_fwd_kernel": 0, "roi_fwd_slices": 1, "roi_fwd_chunks": 2, "nms_sweep_cluster": 3,
+             "proposals_cluster": 4, "roi_fwd_threads": 5}
+ROI_FWD_KERNELS = {"auto": 0, "direct": 1, "tiled": 2, "band": 3, "sorted": 4}
+
+
+def set_tuning(key, value):
+    """Process-wide tuning switch (tests, experiments); returns the previous value.
+    key: a name of TUNE_KEYS; value: int, or a kernel name for 'roi_fwd_kernel'."""
+    k = TUNE_KEYS[key]
+    if isinstance(value, str):
+        value = ROI_FWD_KERNELS[value]
+    prev = lib().wssdl_get_tuning(k)
+    check(lib().wssdl_set_tuning(k, int(value)), "wssdl_set_tuning")
+    return prev
 
 
 def check(code, where):

@@ -21,6 +21,9 @@
     if (_e != cudaSuccess) return (int)_e;      \
   } while (0)
 
+// Process-wide tuning switch (capi.cu; include/wssdl_b200.h: wssdl_set_tuning).
+int wssdl_tuning(int key);
+
 static inline cudaStream_t to_cuda(wssdl_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

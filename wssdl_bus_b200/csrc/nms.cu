@@ -473,8 +473,8 @@ int run_nms(const float* dets, int N, int stride, double thresh, int mode, int m
   // 3.45 / 4.18, 100 000: 11.8 / 12.6.  Default: cluster from N = 65 536.
   // WSSDL_NMS_SWEEP_CLUSTER=0|1 overrides.
   constexpr int SWEEP_CS = 8;
-  const char* cenv = getenv("WSSDL_NMS_SWEEP_CLUSTER");
-  const bool clustered = cenv ? (cenv[0] == '1') : (col_blocks >= 1024);
+  const int ctune = wssdl_tuning(WSSDL_TUNE_NMS_SWEEP_CLUSTER);
+  const bool clustered = ctune >= 0 ? (ctune == 1) : (col_blocks >= 1024);
   const size_t sweep_smem = sizeof(unsigned long long) * (size_t)col_blocks;
   if (sweep_smem > 48 * 1024) {                     // N > 393 216: opt in to the large carve-out
     if (clustered)

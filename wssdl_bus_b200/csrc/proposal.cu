@@ -505,8 +505,8 @@ extern "C" int wssdl_proposals(const float* cls_prob, const float* bbox_pred,
   // step is small and 16 clusters compete for GPC slots), hence: up to 4 images always, up to
   // 18 images when the keep list is long.  WSSDL_PROPOSALS_CLUSTER=0|1 overrides.
   constexpr int CSZ = 8;
-  const char* cenv = getenv("WSSDL_PROPOSALS_CLUSTER");
-  const bool clustered = cenv ? (cenv[0] == '1')
+  const int ctune = wssdl_tuning(WSSDL_TUNE_PROPOSALS_CLUSTER);
+  const bool clustered = ctune >= 0 ? (ctune == 1)
                               : ((long long)B * CSZ <= WSSDL_NUM_SMS &&
                                  (B <= 4 || post_nms_topN >= 1024));
   if (clustered)

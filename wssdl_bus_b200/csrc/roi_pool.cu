@@ -31,6 +31,9 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "roi_pool_dev.cuh"
+
+using namespace wssdl_roi;
 
 namespace {
 
@@ -191,42 +194,12 @@ roi_pool_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
 //     the caller's workspace.  Bucket B collects RoIs whose batch index is outside [0,B):
 //     they produce (0,-1) without touching the map.
 
-// Exact unsigned division by a runtime constant d >= 1 for n < 2^31 (Granlund-Montgomery
-// round-up magic: l = ceil(log2 d), m = ceil(2^(31+l)/d) < 2^32, q = (n*m) >> (31+l)).
-struct FastDiv {
-  unsigned mul, shift;
-};
-FastDiv make_fastdiv(unsigned d) {
-  unsigned l = 0;
-  while ((1ull << l) < d) ++l;
-  FastDiv f;
-  f.mul = (unsigned)(((1ull << (31 + l)) + d - 1) / d);
-  f.shift = 31 + l;
-  return f;
-}
-__device__ __forceinline__ unsigned fastdiv(unsigned n, FastDiv f) {
-  return (unsigned)(((unsigned long long)n * f.mul) >> f.shift);
-}
-
 
 constexpr int T_SLICE = 16;             // channels per CTA
 constexpr int T_LANES = T_SLICE / 4;    // float4 lanes per cell
 constexpr int T_THREADS = 1024;
 constexpr int T_SCAN_MAX_R = 4096;      // in-CTA RoI list capacity (scan mode)
 constexpr int T_MAX_RB = 1024;          // RoIs whose bin edges are resident at a time
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
-__device__ __forceinline__ int roi_bucket(float batch, int B) {
-  const int b = (int)batch;             // same conversion as roi_cells()
-  return (b >= 0 && b < B) ? b : B;
-}
 
 // Counting sort of RoI indices by image: img_start[B+2] (exclusive offsets, bucket B collects
 // the RoIs with no valid image), perm[R] (RoI indices grouped by bucket; the order inside a
@@ -311,51 +284,6 @@ roi_scatter_kernel(const float* __restrict__ rois, int R, int B, int* __restrict
   }
 }
 
-// First-maximum update with the two conditional moves on the FMA pipe.  FSETP, FSEL and SEL
-// all issue to the half-rate ALU pipe (16 lanes/clk per scheduler), which is what bounded
-// the tiled kernel (ncu: math_pipe_throttle, ALU 70 %, FMA 20 %).  `@p FMUL m, v, 1.0f` and
-// `@p IMAD mi, cell, 1, 0` are exact, run on the full-rate FP32 pipe / the FMA-heavy pipe,
-// and leave one ALU instruction (the compare) per element.  `one_f` / `one_i` come from
-// kernel parameters so ptxas cannot fold the multiplications back into selects; the eight
-// channels of a thread use eight distinct integer ones, otherwise ptxas merges their
-// common cell*1 product and falls back to SEL.
-struct Ones {
-  float f;
-  int i[8];
-};
-__device__ __forceinline__ void upd_fma(float v, int cell, float& m, int& mi, float one_f,
-                                        int one_i) {
-  asm("{\n\t.reg .pred p;\n\t"
-      "setp.gt.f32 p, %2, %0;\n\t"            // strict '>' (cc:187): NaN never wins
-      "@p mul.rn.f32 %0, %2, %4;\n\t"
-      "@p mad.lo.s32 %1, %3, %5, 0;\n\t}"
-      : "+f"(m), "+r"(mi)
-      : "f"(v), "r"(cell), "f"(one_f), "r"(one_i));
-}
-
-// 256-bit global stores (sm_100a: STG.E.256): one lane writes 8 consecutive channels, the
-// two lanes of a bin column fill a 64 B half line in one LSU wavefront.
-template <bool STREAM_ST>
-__device__ __forceinline__ void st256(float* p, const float4 a, const float4 b) {
-  if (STREAM_ST)
-    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x),
-                 "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
-  else
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x),
-                 "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
-}
-template <bool STREAM_ST>
-__device__ __forceinline__ void st256(int* p, const int4 a, const int4 b) {
-  if (STREAM_ST)
-    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x),
-                 "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
-  else
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x),
-                 "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
-}
-
-// dynamic shared memory a CTA may ask for: 227 KB minus the kernels' static arrays
-constexpr int T_DYN_SMEM_MAX = 227 * 1024 - 1024;
 constexpr int T_CLASSES = 64;           // RoI cost classes: min(rows/bin,7)*8 + min(cells/row,7)
 
 template <int BIN_MODE, bool STREAM_ST>
@@ -581,38 +509,6 @@ constexpr int B_LANES = B_SLICE / 4;    // float4 chunks per cell
 constexpr int B_THREADS = 1024;
 constexpr int B_SCAN_MAX_R = 4096;
 constexpr int B_MAX_RB = 1024;
-
-// One bin whose rows are not all resident in this band: pooled straight from global memory,
-// one channel at a time.  Rare (RoIs several times taller than the map, never the detector's
-// own proposals), so it is kept out of line and as small in registers as possible: the hot
-// loop's register allocation must not pay for it.  (A vectorised version that stored through
-// the st.v8 inline asm of st256 was narrowed to a scalar store by ptxas 12.9 in some clones of
-// the out-of-line function; caught by the tall-RoI test.)
-template <bool HAS_ARGMAX>
-__device__ __noinline__ void band_slow_bin(const float* __restrict__ img_base, int hs, int he,
-                                           int ws, int nw, int W, int C, int c_lo,
-                                           float* __restrict__ top_o, int* __restrict__ arg_o) {
-#pragma unroll 1
-  for (int k = 0; k < 8; ++k) {
-    float m = -FLT_MAX;
-    int mi = -1;
-#pragma unroll 1
-    for (int h = hs; h < he; ++h) {
-      int idx = (h * W + ws) * C + c_lo + k;
-#pragma unroll 1
-      for (int w = 0; w < nw; ++w, idx += C) {
-        const float v = __ldg(img_base + idx);
-        if (v > m) { m = v; mi = idx; }            // strict '>' (cc:187)
-      }
-    }
-    top_o[k] = m;
-    if (HAS_ARGMAX) arg_o[k] = mi;
-  }
-}
-
-struct BandGeom {
-  int NB, Hb, step;   // bands per image, rows per band, first-row distance of two bands
-};
 
 template <int BIN_MODE, bool HAS_ARGMAX, bool LINEAR>
 __global__ void __launch_bounds__(B_THREADS, 1)
@@ -1089,13 +985,15 @@ struct TiledPlan {
   size_t smem;
 };
 
+}  // namespace
+
 // img_start[B+2] | perm[R] | counts[B+1] | cursor[B+1] | ticket
-size_t tiled_workspace_bytes(int B, int R) {
+size_t wssdl_roi::bucket_workspace_bytes(int B, int R) {
   return sizeof(int) * ((size_t)B + 2 + (size_t)R + 2 * ((size_t)B + 1) + 1) + 16;
 }
 
 // Groups the RoIs by image into the caller's workspace (see roi_hist_kernel).
-cudaError_t launch_roi_bucket(const float* rois, int R, int B, void* workspace, cudaStream_t s,
+cudaError_t wssdl_roi::launch_roi_bucket(const float* rois, int R, int B, void* workspace, cudaStream_t s,
                               int** img_start_out, int** perm_out) {
   int* img_start = static_cast<int*>(workspace);
   int* perm = img_start + (B + 2);
@@ -1114,13 +1012,15 @@ cudaError_t launch_roi_bucket(const float* rois, int R, int B, void* workspace, 
   return cudaGetLastError();
 }
 
+namespace {
+
 TiledPlan plan_tiled(int B, int H, int W, int C, int R, int PH, int PW, bool vec4,
                      size_t workspace_bytes) {
   TiledPlan p = {false, false, 0, 1, 0};
   if (!vec4 || C % T_SLICE != 0 || H > 65535 || W > 65535 || B + 1 > 65535) return p;
   if (PH <= 0 || PW <= 0) return p;
   p.scan = R <= T_SCAN_MAX_R;
-  if (!p.scan && workspace_bytes < tiled_workspace_bytes(B, R)) return p;
+  if (!p.scan && workspace_bytes < bucket_workspace_bytes(B, R)) return p;
   const size_t map_bytes = (size_t)H * W * T_SLICE * sizeof(float);
   const size_t list_bytes = p.scan ? sizeof(int) * (size_t)R : 0;
   const size_t budget = T_DYN_SMEM_MAX;
@@ -1157,7 +1057,7 @@ BandPlan plan_band(int B, int H, int W, int C, int R, int PH, int PW, bool align
   if (!aligned || C % B_SLICE != 0 || H > 65535 || W > 65535 || B + 1 > 65535) return p;
   if (PH <= 0 || PW <= 0 || PH > 255 || H <= 0 || W <= 0) return p;
   p.scan = R <= B_SCAN_MAX_R;
-  if (!p.scan && workspace_bytes < tiled_workspace_bytes(B, R)) return p;
+  if (!p.scan && workspace_bytes < bucket_workspace_bytes(B, R)) return p;
   const size_t row_bytes = (size_t)W * B_SLICE * sizeof(float);
   const size_t list_bytes = p.scan ? sizeof(int) * (size_t)R : 0;
   const size_t per_roi = sizeof(int) * ((size_t)PH + PW + 3);
@@ -1190,66 +1090,50 @@ BandPlan plan_band(int B, int H, int W, int C, int R, int PH, int PW, bool align
   return p;
 }
 
-// Opt a kernel into 227 KB of dynamic shared memory once per device (the attribute is
-// per device; one process may drive several).
-template <typename K>
-cudaError_t allow_big_smem(K kernel, unsigned long long* done_mask) {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
-  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_DYN_SMEM_MAX);
-  if (e == cudaSuccess) __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
-  return e;
-}
-
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 }  // namespace
 
 namespace {
 
+// bucket lists of the band / tiled kernels, or everything the sorted-bins kernels need
+size_t fwd_workspace_bytes(int B, int R, int PH, int PW) {
+  const size_t a = bucket_workspace_bytes(B, R), b = bins_workspace_bytes(B, R, PH, PW);
+  return a > b ? a : b;
+}
+
 // Which forward kernel a call takes, and its launch geometry.  One function for the launcher
 // and for the host-only query wssdl_roi_pool_fwd_plan (CPU tests check the invariants).
-enum { FWD_DIRECT = 0, FWD_TILED = 1, FWD_BAND = 2 };
+enum { FWD_DIRECT = 0, FWD_TILED = 1, FWD_BAND = 2, FWD_BINS = 3 };
 struct FwdChoice {
   int kernel;
   TiledPlan tp;
   BandPlan bp;
+  BinsPlan np;
 };
 
-// force: 0 = by shape, 1 = direct, 2 = tiled, 3 = band (WSSDL_ROI_FWD_KERNEL).  aligned = the
-// pointer requirements of the shared-memory kernels hold (16 B inputs, 32 B outputs, C % 4).
+// force: 0 = by shape, 1 = direct, 2 = tiled, 3 = band, 4 = sorted bins
+// (WSSDL_TUNE_ROI_FWD_KERNEL).  aligned = the pointer requirements of the shared-memory kernels
+// hold (16 B inputs, 32 B outputs, C % 4).
 FwdChoice choose_fwd(int B, int H, int W, int C, int R, int PH, int PW, bool aligned,
                      size_t workspace_bytes, int force) {
   FwdChoice c;
   c.kernel = FWD_DIRECT;
   c.tp = plan_tiled(B, H, W, C, R, PH, PW, aligned, workspace_bytes);
   c.bp = plan_band(B, H, W, C, R, PH, PW, aligned, workspace_bytes);
+  c.np = plan_bins(B, H, W, C, R, PH, PW, aligned, workspace_bytes,
+                   wssdl_tuning(WSSDL_TUNE_ROI_FWD_THREADS));
+  const int sl = wssdl_tuning(WSSDL_TUNE_ROI_FWD_SLICES), ch = wssdl_tuning(WSSDL_TUNE_ROI_FWD_CHUNKS);
+  if (sl > 0 && sl <= C / 32) c.np.sg = sl;
+  if (ch > 0 && (long long)ch * c.np.g.NB <= 65535) c.np.nchunks = ch;
+  // the shared-memory kernels pay where RoIs re-read the map and bins are small (7x7-like);
+  // big bins (C3 14x14x1024) run the direct kernel at the HBM roofline already
   const bool reuse = PH * PW <= 64 && (long long)R * PH * PW * 2 >= (long long)B * H * W;
-  // The tiled kernel (profiles/history/r01_roi_fwd_direct_vs_tiled.txt) wins over the direct
-  // one for one or two images, ties at 256 images and loses when bins are large: tiled while
-  // its grid fits one wave.  Since the band kernel it only takes what that one cannot
-  // (C % 32 != 0).
+  // The tiled kernel only takes what the 32-channel kernels cannot (C % 32 != 0), while its
+  // grid fits one wave (profiles/history/r01_roi_fwd_direct_vs_tiled.txt).
   const bool tiled_pays = c.tp.scan && reuse &&
                           (long long)(C / T_SLICE) * B * c.tp.nchunks <= WSSDL_NUM_SMS;
-  // The band kernel (128 B cells: conflict-free loads, full-line stores) is the default
-  // wherever RoIs re-read the map and bins are small (7x7-like).  Measured on B200
-  // (profiles/r01_roi_fwd_direct_vs_tiled_vs_band.txt): C4 256 images 3.45 ms vs 3.64 direct /
-  // 3.54 tiled; C1 31.7 us vs 38 / 35; C2 24.6 us vs 36 / 29.  It loses where its grid is a
-  // few ragged waves (16 images: 512 CTAs = 3.5 waves, 0.268 vs 0.250 ms direct) and on big
-  // bins (C3 14x14x1024: the direct kernel already runs at the HBM roofline), so: one wave
-  // or at least 8.
-  const long long band_ctas =
-      (long long)(C / B_SLICE) * (B > 0 ? B : 1) * c.bp.g.NB * c.bp.nchunks;
-  const bool band_pays = reuse && c.bp.g.NB <= 4 &&
-                         (band_ctas <= WSSDL_NUM_SMS || band_ctas >= 8ll * WSSDL_NUM_SMS);
-  if (c.bp.ok && (force == 3 || (force == 0 && band_pays))) c.kernel = FWD_BAND;
-  else if (c.tp.ok && force != 1 && (force == 2 || tiled_pays)) c.kernel = FWD_TILED;
+  if (c.np.ok && c.np.g.NB <= 4 && (force == 4 || (force == 0 && reuse))) c.kernel = FWD_BINS;
+  else if (c.bp.ok && force == 3) c.kernel = FWD_BAND;
+  else if (c.tp.ok && force != 1 && (force == 2 || (force == 0 && tiled_pays))) c.kernel = FWD_TILED;
   return c;
 }
 
@@ -1258,12 +1142,16 @@ FwdChoice choose_fwd(int B, int H, int W, int C, int R, int PH, int PW, bool ali
 extern "C" int wssdl_roi_pool_fwd_plan(int B, int H, int W, int C, int R, int PH, int PW,
                                        int with_workspace, int force, int* out) {
   if (!out || B < 0 || H < 0 || W < 0 || C < 0 || R < 0 || PH < 0 || PW < 0) return WSSDL_EINVAL;
-  if (force < 0 || force > 3) return WSSDL_EINVAL;
-  const size_t ws = with_workspace ? tiled_workspace_bytes(B, R) : 0;
+  if (force < 0 || force > 4) return WSSDL_EINVAL;
+  const size_t ws = with_workspace ? fwd_workspace_bytes(B, R, PH, PW) : 0;
   const FwdChoice c = choose_fwd(B, H, W, C, R, PH, PW, C % 4 == 0, ws, force);
-  for (int i = 0; i < 8; ++i) out[i] = 0;
+  for (int i = 0; i < 10; ++i) out[i] = 0;
   out[0] = c.kernel;
-  if (c.kernel == FWD_BAND) {
+  if (c.kernel == FWD_BINS) {
+    out[1] = c.np.g.NB; out[2] = c.np.g.Hb; out[3] = c.np.g.step; out[4] = c.np.nchunks;
+    out[5] = c.np.sort_rch; out[6] = (int)c.np.smem; out[7] = c.np.scan ? 1 : 0;
+    out[8] = c.np.sg; out[9] = c.np.threads;
+  } else if (c.kernel == FWD_BAND) {
     out[1] = c.bp.g.NB; out[2] = c.bp.g.Hb; out[3] = c.bp.g.step; out[4] = c.bp.nchunks;
     out[5] = c.bp.RB; out[6] = (int)c.bp.smem; out[7] = c.bp.scan ? 1 : 0;
   } else if (c.kernel == FWD_TILED) {
@@ -1273,9 +1161,9 @@ extern "C" int wssdl_roi_pool_fwd_plan(int B, int H, int W, int C, int R, int PH
   return WSSDL_OK;
 }
 
-extern "C" size_t wssdl_roi_pool_fwd_workspace_bytes(int B, int R) {
+extern "C" size_t wssdl_roi_pool_fwd_workspace_bytes(int B, int R, int PH, int PW) {
   if (B < 0 || R < 0) return 0;
-  return tiled_workspace_bytes(B, R);
+  return fwd_workspace_bytes(B, R, PH, PW);
 }
 
 extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B, int H, int W,
@@ -1293,17 +1181,19 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
                     (argmax == nullptr || aligned16(argmax));
   cudaStream_t s = to_cuda(stream);
 
-  // Kernel choice (choose_fwd above).  Experiments: WSSDL_ROI_FWD_KERNEL=direct|tiled|band
-  // (read per call so tests can force a kernel), WSSDL_ROI_FWD_STREAM_ST=0|1.
-  const char* kenv = getenv("WSSDL_ROI_FWD_KERNEL");
-  const int force = !kenv ? 0 : (kenv[0] == 'd' ? 1 : (kenv[0] == 't' ? 2 : (kenv[0] == 'b' ? 3 : 0)));
-  const int stream_st = env_int("WSSDL_ROI_FWD_STREAM_ST", 1);
+  // Kernel choice (choose_fwd above); WSSDL_TUNE_ROI_FWD_KERNEL forces one (tests, experiments).
+  const int force = wssdl_tuning(WSSDL_TUNE_ROI_FWD_KERNEL);
   if (workspace == nullptr) workspace_bytes = 0;
   // the shared-memory kernels store 256 bits per lane: outputs must be 32-byte aligned
   const bool al32 = ((reinterpret_cast<uintptr_t>(top) | reinterpret_cast<uintptr_t>(argmax)) & 31u) == 0;
   const FwdChoice choice = choose_fwd(B, H, W, C, R, PH, PW, vec4 && al32, workspace_bytes, force);
   const TiledPlan& tp = choice.tp;
   const BandPlan& bp = choice.bp;
+  if (choice.kernel == FWD_BINS) {
+    WSSDL_RETURN_IF_CUDA(launch_fwd_bins(choice.np, bottom, rois, B, H, W, C, R, PH, PW,
+                                         spatial_scale, bin_mode, top, argmax, workspace, s));
+    return WSSDL_OK;
+  }
   if (choice.kernel == FWD_BAND) {
     int* img_start = nullptr;
     int* perm = nullptr;
@@ -1358,24 +1248,16 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
         bottom, rois, perm, img_start, B, H, W, C, R, PH, PW, spatial_scale, tp.RB, dPW, ones,  \
         top, argmax);                                                                          \
   } while (0)
-    if (bin_mode == WSSDL_BIN_CPU_TRUNC) {
-      if (stream_st) LAUNCH_TILED(WSSDL_BIN_CPU_TRUNC, true);
-      else LAUNCH_TILED(WSSDL_BIN_CPU_TRUNC, false);
-    } else {
-      if (stream_st) LAUNCH_TILED(WSSDL_BIN_GPU_CEIL, true);
-      else LAUNCH_TILED(WSSDL_BIN_GPU_CEIL, false);
-    }
+    if (bin_mode == WSSDL_BIN_CPU_TRUNC) LAUNCH_TILED(WSSDL_BIN_CPU_TRUNC, true);
+    else LAUNCH_TILED(WSSDL_BIN_GPU_CEIL, true);
 #undef LAUNCH_TILED
     WSSDL_CHECK_LAUNCH();
     return WSSDL_OK;
   }
 
   const int CV = vec4 ? C / 4 : C;
-  // channel vectors per thread: 2 when the channel count allows it (tuning knob for
-  // experiments: WSSDL_ROI_FWD_VPT=1|2)
-  const int vpt_env = env_int("WSSDL_ROI_FWD_VPT", 0);
-  int vpt = (vec4 && CV % 64 == 0) ? 2 : 1;
-  if (vpt_env == 1) vpt = 1;
+  // channel vectors per thread: 2 when the channel count allows it
+  const int vpt = (vec4 && CV % 64 == 0) ? 2 : 1;
   const int lanes = CV / vpt;
   dim3 block(pick_block_x(lanes), 1);
   block.y = max(1, min(PW, 128 / (int)block.x));

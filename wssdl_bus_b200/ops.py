@@ -88,7 +88,7 @@ def roi_pool_forward(bottom, rois, pooled_height, pooled_width, spatial_scale, b
         top = torch.empty((R, pooled_height, pooled_width, C), dtype=torch.float32,
                           device=bottom.device)
         argmax = torch.empty_like(top, dtype=torch.int32) if need_argmax else None
-        ws = _workspace(_lib.lib().wssdl_roi_pool_fwd_workspace_bytes(B, R), bottom.device)
+        ws = _workspace(_lib.lib().wssdl_roi_pool_fwd_workspace_bytes(B, R, pooled_height, pooled_width), bottom.device)
         rc = _lib.lib().wssdl_roi_pool_fwd(_ptr(bottom), _ptr(rois), B, H, W, C, R, pooled_height,
                                            pooled_width, float(spatial_scale), _bin_mode(bin_mode),
                                            _ptr(top), _ptr(argmax), _vp(ws.data_ptr()), ws.numel(),
