@@ -34,21 +34,26 @@ int main() {
   cudaMalloc(&d_order, (size_t)NCTA * bins_per_cta * 4);
   std::mt19937 rng(1);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const int Ks[] = {0, 1, 7, 49, 392, 2450};
-  for (int K : Ks) {
+  const int Ks[] = {0, 1, 2, 4, 7, 16, 49, -49, -196, -392, -784, -1568, -3675};
+  for (int K0 : Ks) {
+    const bool shuffle_inside = K0 < 0;   // negative: ascending block order, random order inside a block
+    const int K = K0 < 0 ? -K0 : K0;
     std::vector<unsigned> order((size_t)NCTA * bins_per_cta);
     for (int c = 0; c < NCTA; ++c) {
       const unsigned base = (unsigned)((c / 2) * PER_IMG + (c % 2) * (PER_IMG / 2));
       std::vector<unsigned> v(bins_per_cta);
       for (int i = 0; i < bins_per_cta; ++i) v[i] = base + i;
       if (K == 1) std::shuffle(v.begin(), v.end(), rng);
-      else if (K > 1) {   // random order of blocks of K consecutive bins
+      else if (K > 1 && !shuffle_inside) {   // random order of blocks of K consecutive bins
         const int nb = (bins_per_cta + K - 1) / K;
         std::vector<int> blk(nb); for (int i = 0; i < nb; ++i) blk[i] = i;
         std::shuffle(blk.begin(), blk.end(), rng);
         std::vector<unsigned> w; w.reserve(bins_per_cta);
         for (int b : blk) for (int i = b * K; i < std::min((b + 1) * K, bins_per_cta); ++i) w.push_back(base + i);
         v = w;
+      } else if (K > 1) {                    // blocks in ascending order, shuffled inside
+        for (int b = 0; b * K < bins_per_cta; ++b)
+          std::shuffle(v.begin() + b * K, v.begin() + std::min((b + 1) * K, bins_per_cta), rng);
       }
       std::copy(v.begin(), v.end(), order.begin() + (size_t)c * bins_per_cta);
     }
@@ -60,7 +65,7 @@ int main() {
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 10;
     const double bytes = (double)NCTA * bins_per_cta * 16 * 128 * 2;
-    printf("order K=%4d (0 ascending, 1 random, K>1 random blocks of K bins): %.3f ms  %.0f GB/s  (%s)\n", K, ms,
+    printf("order K=%5d (0 ascending, 1 random, K>1 random blocks of K ascending bins, K<0 ascending blocks shuffled inside): %.3f ms  %.0f GB/s  (%s)\n", K0, ms,
            bytes / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
   }
   return 0;

@@ -78,11 +78,11 @@ def test_fwd_kernel_choice_on_the_baseline_shapes():
     # workspace
     p = _plan(256, 38, 50, 512, 256 * 300, 7, 7)
     assert (p["kernel"], p["NB"], p["Hb"], p["step"], p["scan"]) == (SORTED, 2, 23, 15, 0)
-    # C1 / C2 (one image): sorted bins, lists built in-kernel, RoIs split so the grid is one wave
+    # C1 / C2 (one image): one wave of the band kernel (a single launch), lists built in-kernel
     for R in (300, 128):
         p = _plan(1, 38, 50, 512, R, 7, 7)
-        assert p["kernel"] == SORTED and p["scan"] == 1
-        assert -(-(512 // 32) // p["slices"]) * p["NB"] * p["nchunks"] <= 148
+        assert p["kernel"] == BAND and p["scan"] == 1
+        assert (512 // 32) * p["NB"] * p["nchunks"] <= 148
     # 16 / 32 images (the per-rank batches of the strong-scaling run): sorted bins as well
     assert _plan(16, 38, 50, 512, 16 * 300, 7, 7)["kernel"] == SORTED
     assert _plan(32, 38, 50, 512, 32 * 300, 7, 7)["kernel"] == SORTED
@@ -93,8 +93,9 @@ def test_fwd_kernel_choice_on_the_baseline_shapes():
     assert _plan(1, 38, 50, 20, 300, 7, 7)["kernel"] == DIRECT
     # without a workspace: no room for the bin records (band kernel while the lists can be
     # built in-kernel), > 4096 RoIs: nothing to group them with either
-    assert _plan(1, 38, 50, 512, 300, 7, 7, ws=False)["kernel"] in (DIRECT, TILED)
-    assert _plan(1, 38, 50, 512, 300, 7, 7, ws=False, force=3)["kernel"] == BAND
+    assert _plan(1, 38, 50, 512, 300, 7, 7, ws=False)["kernel"] == BAND
+    assert _plan(16, 38, 50, 512, 4000, 7, 7, ws=False)["kernel"] == DIRECT
+    assert _plan(16, 38, 50, 512, 4000, 7, 7, ws=False, force=3)["kernel"] == BAND
     assert _plan(256, 38, 50, 512, 256 * 300, 7, 7, ws=False)["kernel"] == DIRECT
     # forcing
     assert _plan(256, 38, 50, 512, 256 * 300, 7, 7, force=1)["kernel"] == DIRECT
