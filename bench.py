@@ -7,8 +7,11 @@
 One "step" = one pass of the hot path over one batch of synthetic images:
   per image: 17100 anchors -> decode/clip/filter -> top 6000 -> NMS 0.7 -> 300 RoIs ->
   RoI max-pool 7x7 (+argmax) on a 38x50x512 NHWC map          (BASELINE.json configs[3]/[0])
-Images are sharded by image over ranks (weak scaling: --images-per-gpu each); the only
-collective is the NCCL all-gather of the per-image detections at the end of every step.
+The batch is BASELINE.json configs[3]: 256 images, sharded by image over the ranks (image i
+belongs to rank i mod N: strong scaling, 256 / N images per GPU); the only collective is ONE
+NCCL all-gather per step of the per-image detections (boxes + scores + counts in one blob).
+With N > 1 the weak-scaling number (256 images per GPU) is measured as well and reported under
+"weak_scaling".
 
 Printed JSON (rank 0, one line): value = whole-job images/s with inputs resident in HBM;
 e2e = the same through HOST buffers (pinned H2D of every input, D2H of every output inside
@@ -38,16 +41,18 @@ ROI_POOL_FWD_BYTES_PER_IMAGE = (CFG["H"] * CFG["W"] * CFG["C"] * 4 + CFG["post"]
                                 CFG["post"] * CFG["PH"] * CFG["PW"] * CFG["C"] * 8)
 
 
-def workload_config(images_per_gpu, n_gpus):
+def workload_config(global_images, n_gpus):
+    per_gpu = (global_images + n_gpus - 1) // n_gpus
     return {
         "workload": "C4 batched inference: per image 38x50x512 NHWC map, 17100 anchors -> "
                     "top-6000 -> NMS 0.7 -> 300 RoIs -> roi_pool 7x7 fwd+argmax; synthetic "
                     "600x800 images",
-        "images_per_gpu": images_per_gpu,
-        "global_images": images_per_gpu * n_gpus,
-        "parallelism": "image-sharded x%d, all-gather of detections per step (overlapped with the RoI pooling)" % n_gpus,
+        "global_images": global_images,
+        "images_per_gpu": per_gpu,
+        "parallelism": "image i on rank i mod %d; one all-gather of the packed detections per step "
+                       "(overlapped with the RoI pooling)" % n_gpus,
         "l2": "per-step inputs+outputs (%.1f GB/GPU) exceed the 126 MB L2; no flush needed"
-              % (images_per_gpu * (ROI_POOL_FWD_BYTES_PER_IMAGE + CFG["H"] * CFG["W"] * 54 * 4) / 1e9),
+              % (per_gpu * (ROI_POOL_FWD_BYTES_PER_IMAGE + CFG["H"] * CFG["W"] * 54 * 4) / 1e9),
     }
 
 
@@ -88,8 +93,12 @@ def cpu_arm(steps, warmup, sample_images=None):
     cores = max(1, len(os.sched_getaffinity(0)))
     n = sample_images or max(cores, 8)
     n = min(n, 256)
+    # one image through the same code in THIS process first: the reference's compiled libraries
+    # (oracle/_ref/*.so) are then mapped here too, where the driver's loader hook can see them
+    _cpu_worker((8999,))
     ctx = mp.get_context("fork")
-    with ctx.Pool(processes=min(cores, n)) as pool:
+    pool = ctx.Pool(processes=min(cores, n))
+    try:
         for w in range(max(warmup, 0)):
             pool.map(_cpu_worker, [(9000 + i,) for i in range(min(cores, n))])
         times = []
@@ -97,6 +106,9 @@ def cpu_arm(steps, warmup, sample_images=None):
             t0 = time.perf_counter()
             res = pool.map(_cpu_worker, [(1000 * k + i,) for i in range(n)])
             times.append(time.perf_counter() - t0)
+    finally:
+        pool.close()
+        pool.join()
     per_image = float(np.mean([r[0] for r in res]))
     ms_step = 1e3 * float(np.mean(times))
     value = n / (ms_step / 1e3)
@@ -105,7 +117,10 @@ def cpu_arm(steps, warmup, sample_images=None):
               "(1 thread); %.2f s/image/core"
               % (n, min(cores, n), "reference Cython" if oracle.ref.available() else "C-port",
                  roi_kind, per_image))
-    return dict(value=value, unit=UNIT, cores=min(cores, n), kind=kind, sample=sample), ms_step, n
+    native = sorted(os.path.basename(l.split()[-1]) for l in open("/proc/self/maps")
+                    if "/oracle/" in l and l.rstrip().endswith(".so"))
+    return dict(value=value, unit=UNIT, cores=min(cores, n), kind=kind, sample=sample,
+                sample_images=n, native_libs=sorted(set(native))), ms_step, n
 
 
 def run_reference(args):
@@ -116,8 +131,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args.images_per_gpu, args.gpus),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": dict(workload_config(args.images, args.gpus), sample_images=n,
+                       note="throughput of a %d-image sample of the 256-image batch per step" % n),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -186,12 +203,32 @@ def measured_traffic(kernel, images):
     return None, None
 
 
+def fwd_kernel_of(n_images):
+    """The RoI-pool forward kernel wssdl_roi_pool_fwd picks for a batch of n_images images
+    (host-only plan query of the C ABI) and the kernels one forward call launches."""
+    import ctypes
+    from wssdl_bus_b200 import _lib
+    out = (ctypes.c_int * 10)()
+    R = n_images * CFG["post"]
+    _lib.check(_lib.lib().wssdl_roi_pool_fwd_plan(n_images, CFG["H"], CFG["W"], CFG["C"], R, CFG["PH"],
+                                                  CFG["PW"], 1, _lib.lib().wssdl_get_tuning(0), out),
+               "wssdl_roi_pool_fwd_plan")
+    group = 2 if R > 4096 else 0                  # roi_hist_kernel + roi_scatter_kernel
+    name, launches = {
+        0: ("roi_pool_fwd_kernel<4,CPU_TRUNC,128,2>", 1),
+        1: ("roi_pool_fwd_tiled_kernel<CPU_TRUNC>", 1 + group),
+        2: ("roi_pool_fwd_band_kernel<CPU_TRUNC,argmax,linear>", 1 + group),
+        3: ("roi_pool_fwd_bins_kernel<1024,argmax,linear,tma> (+ roi_bin_sort_kernel)", 2 + group),
+    }[out[0]]
+    return name, launches, list(out)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from wssdl_bus_b200 import ops
-    from wssdl_bus_b200.pipeline import (HostPipeline, HotPath, all_gather_blobs,
-                                         bind_to_gpu_numa_node)
+    from wssdl_bus_b200.pipeline import (DetectionBlob, HostPipeline, HotPath, bind_to_gpu_numa_node,
+                                         shard_images)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,12 +239,10 @@ def run_ours(args):
     numa = bind_to_gpu_numa_node(local)      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.images_per_gpu
-    K, Wm = args.steps, args.warmup
-
-    feat, cls, reg, info = make_inputs(B, 100000 * rank)
-    h = [torch.from_numpy(x).pin_memory() for x in (feat, cls, reg, info)]
-    d = [x.to(dev) for x in h]
+    K, Wm = args.steps, max(args.warmup, 3)
+    G = args.images                          # the global batch: image i on rank i mod world
+    mine = shard_images(G, rank, world)
+    B = (G + world - 1) // world             # every rank computes B slots (the last shard is padded)
     hot = HotPath()
     post = hot.post
 
@@ -217,147 +252,173 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    roi_ev = [(ev(), ev()) for _ in range(K)]
-    prop_ev = [(ev(), ev()) for _ in range(K)]
 
-    def step(k=None):
-        if k is not None:
-            prop_ev[k][0].record()
-        p = ops.proposals(d[1], d[2], d[3], hot.base, hot.feat_stride, hot.pre, hot.post,
-                          hot.thresh, hot.min_size)
-        if k is not None:
-            prop_ev[k][1].record()
-        # the detections (boxes, scores, counts) are complete after the proposals: their
-        # all-gather runs on the communicator's stream while the RoI pooling runs on this one
-        works = []
-        if world > 1:
-            gathered, works = all_gather_blobs(hot.detections(p), async_op=True)
-            p["gathered"] = gathered
-        if k is not None:
-            roi_ev[k][0].record()
-        top, argmax = ops.roi_pool_forward(d[0], p["rois"], hot.pooled_h, hot.pooled_w, hot.scale)
-        if k is not None:
-            roi_ev[k][1].record()
-        p["top"], p["argmax"] = top, argmax
-        for w in works:
-            w.wait()                                  # the step ends when the gather has landed
-        return p
+    def device_leg(n_img, seeds, steps, heavy=False):
+        """K steps of proposals -> (async all-gather of the detection blob) -> RoI-pool forward on
+        n_img images resident in HBM.  Returns (ms_total, roi_ms, prop_ms, counts)."""
+        feat = np.concatenate([syn.feature_map(s_, 1, CFG["H"], CFG["W"], CFG["C"]) for s_ in seeds])
+        parts = [syn.rpn_outputs(s_ + 1, 1, CFG["H"], CFG["W"], CFG["A"]) for s_ in seeds]
+        cls = np.concatenate([p_[0] for p_ in parts])
+        reg = np.concatenate([p_[1] for p_ in parts])
+        info = np.concatenate([p_[2] for p_ in parts])
+        if heavy:
+            reg = (reg * 0.1).astype(np.float32)      # sigma 0.05: boxes hug their anchors
+        d = [torch.from_numpy(x).to(dev) for x in (feat, cls, reg, info)]
+        blob = DetectionBlob(n_img, post, device=dev)
+        roi_ev = [(ev(), ev()) for _ in range(steps)]
+        prop_ev = [(ev(), ev()) for _ in range(steps)]
 
-    for _ in range(max(Wm, 3)):
-        p = step()
-    counts = p["counts"].cpu().numpy()
-    del p
-    barrier()
+        def step(k=None):
+            if k is not None:
+                prop_ev[k][0].record()
+            p = ops.proposals(d[1], d[2], d[3], hot.base, hot.feat_stride, hot.pre, hot.post,
+                              hot.thresh, hot.min_size, out=blob.views())
+            if k is not None:
+                prop_ev[k][1].record()
+            # the detections (boxes, scores, counts: one blob) are complete after the proposals:
+            # their all-gather runs on the communicator's stream while the RoI pooling runs here
+            work = None
+            if world > 1:
+                p["gathered"], work = blob.all_gather(async_op=True)
+            if k is not None:
+                roi_ev[k][0].record()
+            top, argmax = ops.roi_pool_forward(d[0], p["rois"], hot.pooled_h, hot.pooled_w, hot.scale)
+            if k is not None:
+                roi_ev[k][1].record()
+            p["top"], p["argmax"] = top, argmax
+            if work is not None:
+                work.wait()                           # the step ends when the gather has landed
+            return p
+
+        for _ in range(Wm):
+            p = step()
+        counts = p["counts"].cpu().numpy()
+        del p
+        barrier()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for k in range(steps):
+            step(k)
+        t1.record()
+        barrier()
+        return (t0.elapsed_time(t1), float(np.mean([a.elapsed_time(b) for a, b in roi_ev])),
+                float(np.mean([a.elapsed_time(b) for a, b in prop_ev])), counts, d)
+
+    # image i of the global batch has seed 7 * i (whatever the number of ranks); pad slots repeat
+    seeds = [7 * int(i) for i in mine] + [7 * int(mine[-1] if len(mine) else 0)] * (B - len(mine))
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    t0, t1 = ev(), ev()
-    t0.record()
-    for k in range(K):
-        step(k)
-    t1.record()
-    barrier()
-    ms_total = t0.elapsed_time(t1)
-    roi_ms = float(np.mean([a.elapsed_time(b) for a, b in roi_ev]))
-    prop_ms = float(np.mean([a.elapsed_time(b) for a, b in prop_ev]))
+    ms_total, roi_ms, prop_ms, counts, d = device_leg(B, seeds, K)
+    clocks = sampler.summary() if sampler else None
+    # proposals where the NMS has to work: boxes that hug their anchors suppress each other heavily
+    heavy = device_leg(B, seeds, max(3, K // 2), heavy=True)
+    heavy_ms = heavy[2]
+    del heavy
+    # weak scaling (256 images per GPU) next to the strong-scaling headline
+    weak = None
+    if world > 1 and not args.no_weak:
+        wseeds = [7 * (256 * rank + i) for i in range(args.weak_images)]
+        wt = device_leg(args.weak_images, wseeds, K)
+        weak = wt[0]
+        del wt
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region
-    e2e = e2e_dev = None
+    e2e_ms = {}
+    e2e_bytes = {}
     if not args.no_e2e:
-        hp = HostPipeline(hot, B, CFG["H"], CFG["W"], CFG["C"], CFG["A"], chunk=args.e2e_chunk,
-                          device=dev)
-        for _ in range(2):
-            out = hp.run(*h)
-        barrier()
-        e0, e1 = ev(), ev()
-        e0.record()
-        for _ in range(K):
-            out = hp.run(*h)
-            if world > 1:
-                all_gather_blobs([out["rois"].view(B, post, 5).to(dev, non_blocking=True),
-                                  out["scores"].view(B, post).to(dev, non_blocking=True),
-                                  out["counts"].to(dev, non_blocking=True)])
-        e1.record()
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
-        e2e = (e2e_ms, hp.h2d_bytes, hp.d2h_bytes)
-        # same call, pooled features left on the device (the reference's arrangement: fc6
-        # consumes them on the GPU, only the RoIs cross the py_func boundary)
-        del hp, out
-        hp2 = HostPipeline(hot, B, CFG["H"], CFG["W"], CFG["C"], CFG["A"], chunk=args.e2e_chunk,
-                           device=dev, features_to_host=False)
-        for _ in range(2):
-            hp2.run(*h)
-        barrier()
-        f0, f1 = ev(), ev()
-        f0.record()
-        for _ in range(K):
-            out2 = hp2.run(*h)
-            if world > 1:
-                all_gather_blobs([out2["rois"].view(B, post, 5).to(dev, non_blocking=True),
-                                  out2["scores"].view(B, post).to(dev, non_blocking=True),
-                                  out2["counts"].to(dev, non_blocking=True)])
-        f1.record()
-        barrier()
-        e2e_dev = (f0.elapsed_time(f1), hp2.h2d_bytes, hp2.d2h_bytes)
-    clocks = sampler.summary() if sampler else None
+        h = [x.cpu().pin_memory() for x in d]
+        variants = [("e2e", dict()), ("e2e_no_argmax", dict(need_argmax=False)),
+                    ("e2e_features_on_device", dict(features_to_host=False))]
+        for name, kw in variants:
+            hp = HostPipeline(hot, B, CFG["H"], CFG["W"], CFG["C"], CFG["A"], chunk=args.e2e_chunk,
+                              device=dev, **kw)
+            gb = DetectionBlob(B, post, device=dev)
+
+            def e2e_step():
+                out = hp.run(*h)
+                if world > 1:
+                    r_, s_, c_ = gb.views()
+                    r_.copy_(out["rois"], non_blocking=True)
+                    s_.copy_(out["scores"], non_blocking=True)
+                    c_.copy_(out["counts"], non_blocking=True)
+                    gb.all_gather()
+                return out
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(K):
+                e2e_step()
+            e1.record()
+            barrier()
+            e2e_ms[name] = e0.elapsed_time(e1)
+            e2e_bytes[name] = (hp.h2d_bytes, hp.d2h_bytes)
+            del hp, gb
 
     # max over ranks
-    t = torch.tensor([ms_total, roi_ms, prop_ms, e2e[0] if e2e else 0.0,
-                      e2e_dev[0] if e2e else 0.0], device=dev, dtype=torch.float64)
+    names = ["ms_total", "roi_ms", "prop_ms", "heavy_ms", "weak"] + sorted(e2e_ms)
+    vals = [ms_total, roi_ms, prop_ms, heavy_ms, weak or 0.0] + [e2e_ms[k] for k in sorted(e2e_ms)]
+    t = torch.tensor(vals, device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, roi_ms, prop_ms, e2e_ms, e2e_dev_ms = [float(v) for v in t.tolist()]
+    r = dict(zip(names, [float(v) for v in t.tolist()]))
     if rank == 0:
-        ms_step = ms_total / K
-        value = world * B / (ms_step / 1e3)
+        ms_step = r["ms_total"] / K
+        value = G / (ms_step / 1e3)
         peak, peak_src = measured_peak()
-        achieved = B * ROI_POOL_FWD_BYTES_PER_IMAGE / (roi_ms / 1e3) / 1e9
-        # wssdl_roi_pool_fwd picks the band kernel for this workload (csrc/roi_pool.cu);
-        # WSSDL_ROI_FWD_KERNEL=direct|tiled forces the other two
-        kenv = os.environ.get("WSSDL_ROI_FWD_KERNEL", "")
-        kname, ktmpl, nlaunch = {
-            "d": ("roi_pool_fwd_kernel", "<4,CPU_TRUNC,128,2>", 2),
-            "t": ("roi_pool_fwd_tiled_kernel", "<CPU_TRUNC>", 4),
-        }.get(kenv[:1], ("roi_pool_fwd_band_kernel", "<CPU_TRUNC,argmax,linear>", 4))
-        traffic, traffic_src = measured_traffic(kname, B)
+        achieved = B * ROI_POOL_FWD_BYTES_PER_IMAGE / (r["roi_ms"] / 1e3) / 1e9
+        kname, roi_launches, plan = fwd_kernel_of(B)
+        traffic, traffic_src = measured_traffic(kname.split("<")[0], B)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": max(Wm, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(B, world),
-            "roofline": {"kernel": kname + ktmpl,
+            "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(G, world),
+            "roofline": {"kernel": kname,
                          "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
                          "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": B * ROI_POOL_FWD_BYTES_PER_IMAGE,
-                         "ms_per_launch": roi_ms},
-            "kernels_ms_per_step": {"proposals_kernel": prop_ms, "roi_pool_fwd_kernel": roi_ms},
-            # proposals_kernel + roi_pool_fwd kernel (+ roi_hist_kernel and roi_scatter_kernel
-            # when a shared-memory kernel groups the RoIs by image; their few us are inside
-            # ms_per_launch) per step
-            "gpu_launches": nlaunch * K,
+                         "images_per_launch": B,
+                         "ms_per_launch": r["roi_ms"],
+                         "note": "ms_per_launch covers the whole wssdl_roi_pool_fwd call of one rank "
+                                 "(RoI grouping, bin sort pre-pass and pooling kernel)"},
+            "kernels_ms_per_step": {"proposals_kernel": r["prop_ms"], "roi_pool_fwd": r["roi_ms"],
+                                    "proposals_heavy": r["heavy_ms"]},
+            "kernels_note": "proposals_heavy: the same proposals call on regression deltas of sigma "
+                            "0.05 (boxes hug their anchors, the fused NMS visits thousands of "
+                            "candidates before it has kept 300); not part of the timed step",
+            # proposals_kernel + the kernels of one wssdl_roi_pool_fwd call, per step
+            "gpu_launches": (1 + roi_launches) * K,
             "clocks": clocks,
             "rois_per_image": [int(counts.min()), int(counts.max())],
             "numa_node_rank0": numa,
         }
-        if e2e:
-            ems = e2e_ms / K
-            line["e2e"] = {"value": world * B / (ems / 1e3), "unit": UNIT,
-                           "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
-                           "ms_per_step": ems,
-                           "note": "pinned host inputs -> device -> all outputs (rois, scores, "
-                                   "counts, pooled features, argmax) back to pinned host, "
-                                   "chunked over 2 streams; bound by the PCIe D2H copy of the "
-                                   "pooled features"}
-            dms = e2e_dev_ms / K
-            line["e2e_features_on_device"] = {
-                "value": world * B / (dms / 1e3), "unit": UNIT, "h2d_bytes_per_step": e2e_dev[1],
-                "d2h_bytes_per_step": e2e_dev[2], "ms_per_step": dms,
-                "note": "same call and kernels; pooled features + argmax stay in HBM for the "
-                        "next layer (the reference's TF graph does the same), RoIs/scores/counts "
-                        "return to pinned host"}
+        if weak:
+            wms = r["weak"] / K
+            line["weak_scaling"] = {"images_per_gpu": args.weak_images,
+                                    "global_images": args.weak_images * world,
+                                    "value": args.weak_images * world / (wms / 1e3), "unit": UNIT,
+                                    "ms_per_step": wms}
+        notes = {
+            "e2e": "pinned host inputs -> device -> all outputs (rois, scores, counts, pooled "
+                   "features, argmax) back to pinned host, chunked over 2 streams; bound by the PCIe "
+                   "D2H copy of the pooled features",
+            "e2e_no_argmax": "the same call with need_argmax=False: C4 is inference, argmax is only "
+                             "consumed by the backward pass; halves the D2H bytes",
+            "e2e_features_on_device": "same call and kernels; pooled features + argmax stay in HBM for "
+                                      "the next layer (the reference's TF graph does the same), "
+                                      "RoIs/scores/counts return to pinned host",
+        }
+        for name in sorted(e2e_ms):
+            ems = r[name] / K
+            line[name] = {"value": G / (ems / 1e3), "unit": UNIT,
+                          "h2d_bytes_per_step": e2e_bytes[name][0],
+                          "d2h_bytes_per_step": e2e_bytes[name][1], "ms_per_step": ems,
+                          "note": notes[name]}
         if world == 1 and not args.no_cpu_baseline:
             # the CPU arm runs in a fresh process (no CUDA context in the forked workers)
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
@@ -365,12 +426,12 @@ def run_ours(args):
             if args.cpu_sample:
                 cmd += ["--cpu-sample", str(args.cpu_sample)]
             env = dict(os.environ, RANK="0", WORLD_SIZE="1", CUDA_VISIBLE_DEVICES="")
-            r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900,
-                               preexec_fn=lambda: os.sched_setaffinity(0, all_cpus))  # all host cores
+            rr = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900,
+                                preexec_fn=lambda: os.sched_setaffinity(0, all_cpus))  # all host cores
             try:
-                line["cpu_baseline"] = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+                line["cpu_baseline"] = json.loads(rr.stdout.strip().splitlines()[-1])["cpu_baseline"]
             except Exception:
-                line["cpu_baseline"] = {"error": (r.stderr or r.stdout)[-300:]}
+                line["cpu_baseline"] = {"error": (rr.stderr or rr.stdout)[-300:]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -382,7 +443,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images-per-gpu", type=int, default=256)
+    ap.add_argument("--images", type=int, default=256, help="global batch, sharded over the ranks")
+    ap.add_argument("--weak-images", type=int, default=256, help="images per GPU of the weak-scaling leg")
+    ap.add_argument("--no-weak", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")

@@ -218,11 +218,17 @@ int wssdl_bbox_transform(const float* ex_rois, const float* gt_rois, int N, floa
  * counts    [B] i32
  * decoded   [B,H*W*A,4] f32 (may be NULL): every anchor decoded+clipped, row order (h,w,a)
  *           -- the intermediate of :116-119, for inspection and parity tests
- * pre_nms_topN <= 0 means "no truncation" (:130).
+ * nms_mode  WSSDL_NMS_GE_F64 (cpu_nms, what nms_wrapper.nms runs with cfg.USE_GPU_NMS = False,
+ *           the reference's setting) or WSSDL_NMS_GT_F32 (gpu_nms / py_cpu_nms: `>` against the
+ *           float threshold, what it runs with cfg.USE_GPU_NMS = True)
+ * pre_nms_topN <= 0 means "no truncation" (:130); the candidates are sorted lazily, M =
+ * max(1024, pow2ceil(2*post_nms_topN)) at a time (fewer when shared memory is short), so any
+ * pre_nms_topN fits.
  * Limits (WSSDL_ELIMIT otherwise): H*W*A <= 32768 anchors per image, 0 < post_nms_topN <=
- * 4096, and the per-image state must fit one SM's shared memory:
- * 8*pow2ceil(min(pre_nms_topN, H*W*A)) + max(4*H*W*A, 20*post_nms_topN + 17 KB) + 1 KB
- * <= 227 KB (the reference's shapes, 17100 anchors with 6000->300 or 12000->2000, fit).
+ * 4096 (the callers map the reference's "post_nms_topN <= 0: no truncation", :139, onto
+ * min(pre_nms_topN, H*W*A) when that fits), and the per-image state must fit one SM's shared
+ * memory: 8*1024 + 4*H*W*A + 20*post_nms_topN + 18 KB <= 226 KB (17100 anchors with 6000->300,
+ * 12000->2000 or no truncation -> 4096 fit).
  */
 size_t wssdl_proposals_workspace_bytes(int B, int H, int W, int A, int pre_nms_topN,
                                        int post_nms_topN);
@@ -230,7 +236,8 @@ size_t wssdl_proposals_workspace_bytes(int B, int H, int W, int A, int pre_nms_t
 int wssdl_proposals(const float* cls_prob, const float* bbox_pred, const float* im_info,
                     int info_stride, int B, int H, int W, int A, const float* base_anchors,
                     int feat_stride, int pre_nms_topN, int post_nms_topN, double nms_thresh,
-                    float min_size, float* rois, float* scores, int* anchor_idx, int* counts,
+                    int nms_mode, float min_size, float* rois, float* scores, int* anchor_idx,
+                    int* counts,
                     float* decoded, void* workspace, size_t workspace_bytes,
                     wssdl_stream_t stream);
 

@@ -162,13 +162,13 @@ def main():
         emit(out, op="cpu_anchor_labels", B=1, ms=best_of(
             lambda: oracle.layers.anchor_labels(38, 50, gt[0, :num[0]], info[0])))
     if want("proposals"):
-        for B in (1, 16, 256):
+        for B in (1, 16, 32, 64, 128, 256):
             cls, reg, info = syn.rpn_outputs(7, B, 38, 50, 9)
             cls, reg, info = [torch.from_numpy(v).cuda() for v in (cls, reg, info)]
             hot = HotPath()
             for pre, post, tag in ((6000, 300, "TEST 6000->300"), (12000, 2000, "TRAIN 12000->2000"),
                                    (2000, 2000, "C2 2000->2000")):
-                if B == 256 and post == 2000:
+                if B > 16 and post == 2000:
                     continue
                 med, best = timeit(lambda: ops.proposals(cls, reg, info, hot.base, 16, pre, post, 0.7, 16),
                                    iters=10, flush=False)

@@ -37,6 +37,18 @@ elif what == "bwd":
     g = torch.randn_like(top)
     for _ in range(3):
         ops.roi_pool_backward((B, H, W, C), r, arg, g, 14, 14, 1 / 16.)
+elif what.startswith("prop"):
+    # the proposals kernel on the C4 shapes: prop:<images>[:heavy]
+    from wssdl_bus_b200.pipeline import HotPath
+    parts = what.split(":")
+    nimg = int(parts[1]) if len(parts) > 1 else 32
+    cls, reg, info = syn.rpn_outputs(0, nimg, 38, 50, 9)
+    if len(parts) > 2 and parts[2] == "heavy":
+        reg = (reg * 0.1).astype(np.float32)
+    cls, reg, info = [torch.from_numpy(v).cuda() for v in (cls, reg, info)]
+    hot = HotPath()
+    for _ in range(3):
+        ops.proposals(cls, reg, info, hot.base, 16, hot.pre, hot.post, hot.thresh, hot.min_size)
 elif what.startswith("roi4"):
     # the C4 RoI-pool forward launch (256 images x 300 proposal RoIs), 3 launches
     from wssdl_bus_b200 import _lib

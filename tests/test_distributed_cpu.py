@@ -21,8 +21,8 @@ def _worker(rank, world, port, n_images, post, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from wssdl_bus_b200.pipeline import (all_gather_blobs, all_gather_detections, shard_images,
-                                         unshard_detections)
+    from wssdl_bus_b200.pipeline import (DetectionBlob, all_gather_blobs, all_gather_detections,
+                                         shard_images, unshard_detections)
     mine = shard_images(n_images, rank, world)
     n_local = (n_images + world - 1) // world
     det = torch.zeros((n_local, post, 5))
@@ -46,6 +46,20 @@ def _worker(rank, world, port, n_images, post, ret):
     for w in works:
         w.wait()
     ok = ok and torch.equal(b3, boxes) and torch.equal(s3, scores) and torch.equal(c3, counts)
+    # the packed form: boxes + scores + counts of a rank in ONE buffer, one collective
+    blob = DetectionBlob(n_local, post)
+    r_, s_, c_ = blob.views()
+    r_.copy_(det.view(-1, 5))
+    s_.copy_(det[:, :, 4].reshape(-1))
+    c_.copy_(cnt)
+    for async_op in (False, True):
+        (b4, s4, c4), work = blob.all_gather(async_op=async_op)
+        if async_op:
+            work.wait()
+        ok = ok and work is None or async_op
+        ok = ok and torch.equal(b4, boxes) and torch.equal(s4, scores) and torch.equal(c4, counts)
+        d4, cc4 = unshard_detections(b4, c4, n_images)
+        ok = ok and torch.equal(d4, d) and torch.equal(cc4, c)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

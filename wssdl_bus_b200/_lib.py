@@ -41,7 +41,7 @@ SIGNATURES = {
     "wssdl_clip_boxes": (_i, [_vp, _i, _i, _f, _f, _vp]),
     "wssdl_bbox_transform": (_i, [_vp, _vp, _i, _vp, _vp]),
     "wssdl_proposals_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "wssdl_proposals": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _d, _f,
+    "wssdl_proposals": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _d, _i, _f,
                              _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wssdl_detect_postprocess": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _d, _i, _i, _vp, _vp,
                                       _vp, _vp, _vp]),

@@ -11,11 +11,14 @@
 //   1. decode+clip+filter every anchor; keep only a 32-bit orderable score key per anchor
 //      in shared memory (0 = filtered out).  Boxes are NOT stored: they are a pure
 //      function of (anchor index, 4 deltas) and are recomputed bit-identically when needed.
-//   2. radix select (4 x 8-bit histogram passes over the shared keys) of the K-th largest
-//      key, K = min(pre_nms_topN, #valid); ties at the threshold are resolved by a second
-//      select on the anchor index so exactly K survive (score desc, index desc).
-//   3. compaction of the K survivors as 64-bit (~key, ~index) words + in-shared bitonic
-//      sort => the reference's descending-score order.
+//   2./3. the K = min(pre_nms_topN, #valid) best anchors in the reference's order (score desc,
+//      index desc for ties) are produced LAZILY, M at a time: a radix select (4 x 8-bit
+//      histogram passes over the shared keys, a second select on the anchor index for ties at
+//      the threshold) finds the key that bounds the next M candidates, they are compacted as
+//      64-bit (~key, ~index) words and sorted by an in-shared bitonic sort.  The keep-list NMS
+//      below stops as soon as post_nms_topN boxes are kept, which on the detector's shapes
+//      (6000 -> 300) happens inside the first batch: sorting all 6000 (padded to 8192) up front
+//      was 40 % of the kernel (ncu, profiles/r02_proposals.txt).  M = max(1024, pow2 >= 2*post).
 //   4. NMS driven by the keep list instead of an N x N mask: post_nms_topN is small
 //      (300 / 2000) so a candidate only has to be tested against boxes ALREADY KEPT
 //      (<= post_nms_topN) and the loop stops as soon as the list is full.  Candidates are
@@ -49,7 +52,7 @@ struct PropParams {
   int H, W, A, NA;
   int feat_stride;
   int pre_nms_topN, post_nms_topN;
-  int kpad;                      // power of two >= min(pre_nms_topN, NA)
+  int kpad;                      // M: candidates sorted at a time (power of two)
   float thr_ge;                  // smallest float whose double value is >= nms_thresh
   float min_size;
   float* rois;
@@ -200,16 +203,14 @@ proposals_kernel(const PropParams p) {
     cg::this_cluster().sync();
   }
   const bool writer = crank == 0;
-  // layout: sort buffer (kpad u64) | histogram/scalars | UNION { keys (NA u32), live in phases
-  // 1-3 ; per-chunk NMS state + kept list, live in phase 4 }.  The score keys are dead once
-  // the survivors sit in the sort buffer (which carries ~key in its high word).
+  // layout: sort buffer (kpad u64) | histogram/scalars | keys (NA u32, rounded to 4) | per-chunk
+  // NMS state | kept list
   unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem_raw);
   unsigned* s_hist = reinterpret_cast<unsigned*>(s_sort + p.kpad);             // [256]
   unsigned* s_bcast = s_hist + 256;                                            // [4]
   int* s_cnt = reinterpret_cast<int*>(s_bcast + 4);                            // [4]
-  unsigned char* s_union = reinterpret_cast<unsigned char*>(s_cnt + 4);
-  unsigned* s_keys = reinterpret_cast<unsigned*>(s_union);                     // [NA]
-  float4* s_cbox = reinterpret_cast<float4*>(s_union);                         // [CHUNK]
+  unsigned* s_keys = reinterpret_cast<unsigned*>(s_cnt + 4);                   // [NA]
+  float4* s_cbox = reinterpret_cast<float4*>(s_keys + ((p.NA + 3) & ~3));      // [CHUNK]
   unsigned long long* s_col = reinterpret_cast<unsigned long long*>(s_cbox + CHUNK);  // [CHUNK][4]
   float* s_carea = reinterpret_cast<float*>(s_col + CHUNK * 4);                // [CHUNK]
   int* s_cidx = reinterpret_cast<int*>(s_carea + CHUNK);                       // [CHUNK]
@@ -248,46 +249,54 @@ proposals_kernel(const PropParams p) {
   const int n_valid = s_cnt[0];
   const int K = min(p.pre_nms_topN, n_valid);
 
-  // ---- phase 2: threshold key (and threshold index among ties)
-  unsigned T = 0, T2 = 0;
-  if (K < n_valid) {
-    int n_gt = 0;
-    T = radix_select([&](int i) { return s_keys[i]; }, p.NA, K, s_hist, s_bcast, &n_gt);
-    const int need_eq = K - n_gt;             // how many keys == T survive (highest indices)
-    int dummy = 0;
-    T2 = radix_select([&](int i) { return s_keys[i] == T ? (unsigned)(i + 1) : 0u; }, p.NA,
-                      need_eq, s_hist, s_bcast, &dummy);
-  }
-
-  // ---- phase 3: compact survivors + bitonic sort (ascending in (~key, ~index))
-  for (int i = tid; i < p.kpad; i += PT) s_sort[i] = ~0ull;
-  __syncthreads();
-  for (int a = tid; a < p.NA; a += PT) {
-    const unsigned k = s_keys[a];
-    const bool take = (k != 0u) && (k > T || (k == T && (unsigned)(a + 1) >= T2));
-    if (take) {
-      const int pos = atomicAdd(&s_cnt[1], 1);
-      s_sort[pos] = ((unsigned long long)(~k) << 32) | (unsigned)(~(unsigned)a);
-    }
-  }
-  __syncthreads();
-  for (int k = 2; k <= p.kpad; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < p.kpad / 2; t += PT) {
-        const int i = 2 * t - (t & (j - 1));
-        const bool up = ((i & k) == 0);
-        const unsigned long long x = s_sort[i], y = s_sort[i + j];
-        if ((x > y) == up) { s_sort[i] = y; s_sort[i + j] = x; }
-      }
-      __syncthreads();
-    }
-  }
-
-  // ---- phase 4: keep-list NMS over the K sorted candidates
+  // ---- phases 2-4: batches of M candidates in descending order, keep-list NMS over each
+  const int M = p.kpad;
   int nkept = 0;
   int round = 0;
-  for (int c0 = 0; c0 < K && nkept < post; c0 += CHUNK, ++round) {
-    const int nc = min(CHUNK, K - c0);
+  unsigned Tp = 0, T2p = 0;                   // boundary behind the previous batch
+  for (int taken = 0; taken < K && nkept < post; taken += M) {
+    const int want = min(taken + M, K);       // rank of the last candidate of this batch
+    // boundary (T, T2): candidate (k, a) is among the best `want` iff k > T or (k == T and
+    // a + 1 >= T2): key and, among ties at T, the highest indices first
+    unsigned T = 0, T2 = 0;
+    if (want < n_valid) {
+      int n_gt = 0;
+      T = radix_select([&](int i) { return s_keys[i]; }, p.NA, want, s_hist, s_bcast, &n_gt);
+      const int need_eq = want - n_gt;        // how many keys == T are in (highest indices)
+      int dummy = 0;
+      T2 = radix_select([&](int i) { return s_keys[i] == T ? (unsigned)(i + 1) : 0u; }, p.NA,
+                        need_eq, s_hist, s_bcast, &dummy);
+    }
+    // compact this batch + bitonic sort (ascending in (~key, ~index))
+    if (tid == 0) s_cnt[1] = 0;
+    for (int i = tid; i < M; i += PT) s_sort[i] = ~0ull;
+    __syncthreads();
+    for (int a = tid; a < p.NA; a += PT) {
+      const unsigned k = s_keys[a];
+      const bool in_now = (k != 0u) && (k > T || (k == T && (unsigned)(a + 1) >= T2));
+      const bool in_before = taken > 0 && (k > Tp || (k == Tp && (unsigned)(a + 1) >= T2p));
+      if (in_now && !in_before) {
+        const int pos = atomicAdd(&s_cnt[1], 1);
+        s_sort[pos] = ((unsigned long long)(~k) << 32) | (unsigned)(~(unsigned)a);
+      }
+    }
+    __syncthreads();
+    for (int k = 2; k <= M; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < M / 2; t += PT) {
+          const int i = 2 * t - (t & (j - 1));
+          const bool up = ((i & k) == 0);
+          const unsigned long long x = s_sort[i], y = s_sort[i + j];
+          if ((x > y) == up) { s_sort[i] = y; s_sort[i + j] = x; }
+        }
+        __syncthreads();
+      }
+    }
+    Tp = T;
+    T2p = T2;
+    const int nbatch = want - taken;
+  for (int c0 = 0; c0 < nbatch && nkept < post; c0 += CHUNK, ++round) {
+    const int nc = min(CHUNK, nbatch - c0);
     if (tid < CHUNK) {
       if (tid < nc) {
         const unsigned long long e = s_sort[c0 + tid];
@@ -444,6 +453,7 @@ proposals_kernel(const PropParams p) {
     nkept = min(nkept + total_new, post);
     __syncthreads();
   }
+  }
   if constexpr (CS > 1) cg::this_cluster().sync();   // no peer may still write into my slots
   if (!writer) return;
   // zero-fill the unused tail so the blob is deterministic
@@ -457,14 +467,14 @@ proposals_kernel(const PropParams p) {
 
 size_t prop_smem_bytes(int NA, int kpad, int post) {
   const size_t na_pad = (size_t)((NA + 3) & ~3);
-  size_t fixed = sizeof(unsigned long long) * (size_t)kpad;          // s_sort
-  fixed += sizeof(unsigned) * (256 + 4) + sizeof(int) * 4;           // s_hist, s_bcast, s_cnt
-  const size_t keys = sizeof(unsigned) * na_pad;                     // phases 1-3
-  size_t nms = sizeof(float4) * CHUNK + sizeof(unsigned long long) * CHUNK * 4 +
-               sizeof(float) * CHUNK + sizeof(int) * CHUNK + sizeof(unsigned) * CHUNK +
-               sizeof(unsigned) * (CHUNK / 32) * 2;                  // per-chunk state
-  nms += (sizeof(float4) + sizeof(float)) * (size_t)post;            // kept list
-  return fixed + (keys > nms ? keys : nms);
+  size_t total = sizeof(unsigned long long) * (size_t)kpad;          // s_sort
+  total += sizeof(unsigned) * (256 + 4) + sizeof(int) * 4;           // s_hist, s_bcast, s_cnt
+  total += sizeof(unsigned) * na_pad;                                // score keys
+  total += sizeof(float4) * CHUNK + sizeof(unsigned long long) * CHUNK * 4 +
+           sizeof(float) * CHUNK + sizeof(int) * CHUNK + sizeof(unsigned) * CHUNK +
+           sizeof(unsigned) * (CHUNK / 32) * 2;                      // per-chunk NMS state
+  total += (sizeof(float4) + sizeof(float)) * (size_t)post;          // kept list
+  return total;
 }
 
 int pow2ceil(int v) {
@@ -482,11 +492,13 @@ extern "C" size_t wssdl_proposals_workspace_bytes(int, int, int, int, int, int) 
 extern "C" int wssdl_proposals(const float* cls_prob, const float* bbox_pred,
                                const float* im_info, int info_stride, int B, int H, int W, int A,
                                const float* base_anchors, int feat_stride, int pre_nms_topN,
-                               int post_nms_topN, double nms_thresh, float min_size, float* rois,
+                               int post_nms_topN, double nms_thresh, int nms_mode, float min_size,
+                               float* rois,
                                float* scores, int* anchor_idx, int* counts, float* decoded,
                                void* workspace, size_t workspace_bytes, wssdl_stream_t stream) {
   (void)workspace; (void)workspace_bytes;
   if (B < 0 || H <= 0 || W <= 0 || A <= 0 || info_stride < 3) return WSSDL_EINVAL;
+  if (nms_mode != WSSDL_NMS_GE_F64 && nms_mode != WSSDL_NMS_GT_F32) return WSSDL_EINVAL;
   if (B == 0) return WSSDL_OK;
   if (!cls_prob || !bbox_pred || !im_info || !base_anchors || !rois || !counts) return WSSDL_EINVAL;
   const long long NA = (long long)H * W * A;
@@ -494,9 +506,16 @@ extern "C" int wssdl_proposals(const float* cls_prob, const float* bbox_pred,
   if (pre_nms_topN <= 0) pre_nms_topN = (int)NA;        // :130: no truncation
   if (post_nms_topN <= 0 || post_nms_topN > 4096) return WSSDL_ELIMIT;
   if (decoded && !aligned16(decoded)) return WSSDL_EALIGN;
-  const int kpad = pow2ceil((int)((long long)pre_nms_topN < NA ? pre_nms_topN : NA));
+  // candidates sorted at a time: the first batch should usually hold enough to keep `post`
+  const int kmax = pow2ceil((int)((long long)pre_nms_topN < NA ? pre_nms_topN : NA));
+  int kpad = pow2ceil(2 * post_nms_topN);
+  if (kpad < 1024) kpad = 1024;
+  if (kpad > kmax) kpad = kmax;
+  // (1 KB of the 227 KB carve-out is left to the kernels' static arrays)
+  const size_t smem_max = 226 * 1024;
+  while (kpad > 1024 && prop_smem_bytes((int)NA, kpad, post_nms_topN) > smem_max) kpad >>= 1;
   const size_t smem = prop_smem_bytes((int)NA, kpad, post_nms_topN);
-  if (smem > 227 * 1024) return WSSDL_ELIMIT;
+  if (smem > smem_max) return WSSDL_ELIMIT;
   cudaStream_t s = to_cuda(stream);
   // Small batches: a cluster of 8 CTAs per image (see the kernel); a batch that fills the
   // machine by itself keeps one CTA per image.  Measured on B200 (B = 1: TRAIN 12000->2000
@@ -522,8 +541,11 @@ extern "C" int wssdl_proposals(const float* cls_prob, const float* bbox_pred,
   p.info_stride = info_stride; p.H = H; p.W = W; p.A = A; p.NA = (int)NA;
   p.feat_stride = feat_stride; p.pre_nms_topN = pre_nms_topN; p.post_nms_topN = post_nms_topN;
   p.kpad = kpad;
+  // cpu_nms: (double)iou >= thresh  <=>  iou >= the smallest float not below thresh;
+  // gpu_nms / py_cpu_nms: iou > (float)thresh  <=>  iou >= the next float above (float)thresh
   float f = (float)nms_thresh;
-  if ((double)f < nms_thresh) f = nextafterf(f, INFINITY);
+  if (nms_mode == WSSDL_NMS_GT_F32) f = nextafterf(f, INFINITY);
+  else if ((double)f < nms_thresh) f = nextafterf(f, INFINITY);
   p.thr_ge = f;
   p.min_size = min_size;
   p.rois = rois; p.scores = scores; p.anchor_idx = anchor_idx; p.counts = counts;

@@ -327,10 +327,16 @@ def bbox_transform(ex_rois, gt_rois):
 
 # ------------------------------------------------------------------ proposals
 def proposals(cls_prob, bbox_pred, im_info, base_anchors, feat_stride, pre_nms_topN,
-              post_nms_topN, nms_thresh, min_size, want_decoded=False):
+              post_nms_topN, nms_thresh, min_size, want_decoded=False, out=None,
+              nms_mode=NMS_GE_F64):
     """Batched fused proposal layer.  cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A] (NHWC),
     im_info [B,>=3].  Returns dict of device tensors: rois [B*post,5], scores [B*post],
-    anchor_idx [B*post] i32, counts [B] i32 (+ decoded [B,H*W*A,4] when asked)."""
+    anchor_idx [B*post] i32, counts [B] i32 (+ decoded [B,H*W*A,4] when asked).
+    out: optional (rois, scores, counts) tensors to write into (e.g. the views of one
+    contiguous detection blob, pipeline.DetectionBlob, so that one all-gather moves them).
+    nms_mode: NMS_GE_F64 (cpu_nms, cfg.USE_GPU_NMS False) or NMS_GT_F32 (gpu_nms).
+    pre_nms_topN <= 0 / post_nms_topN <= 0: no truncation (proposal_layer_tf_bus.py:130, :139);
+    the stride of the blob is then min(pre_nms_topN or H*W*A, H*W*A) (<= 4096 on the device)."""
     cls_prob = _cuda(cls_prob, torch.float32)
     dev = cls_prob.device
     bbox_pred = _cuda(bbox_pred, torch.float32, dev)
@@ -342,21 +348,33 @@ def proposals(cls_prob, bbox_pred, im_info, base_anchors, feat_stride, pre_nms_t
     B, H, W, C2 = cls_prob.shape
     if C2 != 2 * A or tuple(bbox_pred.shape) != (B, H, W, 4 * A) or im_info.shape[0] != B:
         raise ValueError("shape mismatch: cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A], im_info [B,3+]")
+    NA = H * W * A
     post = int(post_nms_topN)
     if post <= 0:
-        raise ValueError("post_nms_topN must be positive on the device path")
+        post = min(int(pre_nms_topN), NA) if int(pre_nms_topN) > 0 else NA
     with torch.cuda.device(dev):
-        rois = torch.empty((B * post, 5), dtype=torch.float32, device=dev)
-        scores = torch.empty((B * post,), dtype=torch.float32, device=dev)
+        if out is not None:
+            rois, scores, counts = out
+            if (tuple(rois.shape) != (B * post, 5) or tuple(scores.shape) != (B * post,) or
+                    tuple(counts.shape) != (B,) or rois.dtype != torch.float32 or
+                    scores.dtype != torch.float32 or counts.dtype != torch.int32 or
+                    not (rois.is_contiguous() and scores.is_contiguous() and counts.is_contiguous())
+                    or rois.device != dev):
+                raise ValueError("out = (rois [B*post,5] f32, scores [B*post] f32, counts [B] i32), "
+                                 "contiguous, on the inputs' device")
+        else:
+            rois = torch.empty((B * post, 5), dtype=torch.float32, device=dev)
+            scores = torch.empty((B * post,), dtype=torch.float32, device=dev)
+            counts = torch.empty((B,), dtype=torch.int32, device=dev)
         aidx = torch.empty((B * post,), dtype=torch.int32, device=dev)
-        counts = torch.empty((B,), dtype=torch.int32, device=dev)
         decoded = (torch.empty((B, H * W * A, 4), dtype=torch.float32, device=dev)
                    if want_decoded else None)
-        ws = _workspace(256, dev)
+        ws = _workspace(_lib.lib().wssdl_proposals_workspace_bytes(B, H, W, A, int(pre_nms_topN),
+                                                                   post), dev)
         rc = _lib.lib().wssdl_proposals(
             _ptr(cls_prob), _ptr(bbox_pred), _ptr(im_info), im_info.shape[1], B, H, W, A,
             base.ctypes.data_as(_vp), int(feat_stride), int(pre_nms_topN), post,
-            float(nms_thresh), float(min_size), _ptr(rois), _ptr(scores), _ptr(aidx),
+            float(nms_thresh), int(nms_mode), float(min_size), _ptr(rois), _ptr(scores), _ptr(aidx),
             _ptr(counts), _ptr(decoded), _vp(ws.data_ptr()), ws.numel(), _stream(dev))
     _lib.check(rc, "wssdl_proposals")
     out = dict(rois=rois, scores=scores, anchor_idx=aidx, counts=counts, post_nms_topN=post)

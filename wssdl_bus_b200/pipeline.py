@@ -63,11 +63,15 @@ class HotPath:
         # kernels launched by one run(): proposals + roi_pool_fwd
         self.launches_per_run = 2
 
-    def run(self, feat, cls_prob, bbox_pred, im_info, need_argmax=True):
+    def run(self, feat, cls_prob, bbox_pred, im_info, need_argmax=True, blob=None):
         """Device tensors in, device tensors out, no synchronisation.
-        feat [B,H,W,C], cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A], im_info [B,3+]."""
+        feat [B,H,W,C], cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A], im_info [B,3+].
+        blob: a DetectionBlob the proposals are written into (for the all-gather).
+        Rows >= counts[b] of an image's `post` RoI slots are zero RoIs (batch 0, empty box):
+        their pooled rows are defined (the cell (0,0) of image 0) but carry no detection."""
         p = ops.proposals(cls_prob, bbox_pred, im_info, self.base, self.feat_stride, self.pre,
-                          self.post, self.thresh, self.min_size)
+                          self.post, self.thresh, self.min_size,
+                          out=None if blob is None else blob.views())
         top, argmax = ops.roi_pool_forward(feat, p["rois"], self.pooled_h, self.pooled_w,
                                            self.scale, self.bin_mode, need_argmax)
         p["top"], p["argmax"] = top, argmax
@@ -79,6 +83,58 @@ class HotPath:
         are the tensors that are all-gathered."""
         B = p["counts"].shape[0]
         return p["rois"].view(B, self.post, 5), p["scores"].view(B, self.post), p["counts"]
+
+
+class DetectionBlob:
+    """The per-image detections of one rank as ONE contiguous f32 buffer, so that a single
+    all-gather moves them (boxes + scores + counts in one blob):
+
+        [ rois   n_local*post*5 f32 | scores n_local*post f32 | counts n_local i32 ]
+
+    (sections padded to 16 bytes).  `rois`, `scores`, `counts` are views the proposals kernel
+    writes directly (ops.proposals(out=blob.views())): no packing kernel, no concatenation."""
+
+    def __init__(self, n_local, post, device=None, buffer=None):
+        self.n_local, self.post = int(n_local), int(post)
+        r4 = lambda v: (v + 3) // 4 * 4  # noqa: E731
+        self.o_scores = r4(self.n_local * self.post * 5)
+        self.o_counts = self.o_scores + r4(self.n_local * self.post)
+        self.numel = self.o_counts + r4(self.n_local)
+        self.buffer = (torch.zeros((self.numel,), dtype=torch.float32, device=device)
+                       if buffer is None else buffer)
+        assert self.buffer.numel() == self.numel and self.buffer.dtype == torch.float32
+
+    @staticmethod
+    def _split(buf, n_local, post, o_scores, o_counts):
+        lead = tuple(buf.shape[:-1])
+        rois = buf[..., :n_local * post * 5].reshape(lead + (n_local, post, 5))
+        scores = buf[..., o_scores:o_scores + n_local * post].reshape(lead + (n_local, post))
+        counts = buf[..., o_counts:o_counts + n_local].view(torch.int32)
+        return rois, scores, counts
+
+    def views(self):
+        """(rois [n_local*post,5], scores [n_local*post], counts [n_local] i32): views of the buffer."""
+        rois, scores, counts = self._split(self.buffer, self.n_local, self.post, self.o_scores,
+                                           self.o_counts)
+        return rois.view(self.n_local * self.post, 5), scores.view(-1), counts
+
+    def all_gather(self, group=None, async_op=False):
+        """ONE all_gather_into_tensor of the buffer (NCCL over NVLink on GPUs, gloo in the CPU
+        tests).  Returns ((rois [world,n_local,post,5], scores [world,n_local,post], counts
+        [world,n_local] i32), work-or-None); image of slot (r, j) is j*world + r under
+        shard_images().  With async_op the collective runs on the communicator's stream behind
+        the work already enqueued on the current one; wait() before reading."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            g, work = self.buffer[None], None
+        else:
+            g = torch.empty((world * self.numel,), dtype=torch.float32, device=self.buffer.device)
+            work = dist.all_gather_into_tensor(g, self.buffer, group=group, async_op=async_op)
+            g = g.view(world, self.numel)
+            if not async_op:
+                work = None
+        return self._split(g, self.n_local, self.post, self.o_scores, self.o_counts), work
 
 
 def all_gather_blobs(tensors, group=None, async_op=False):
@@ -168,6 +224,7 @@ class HostPipeline:
                           cls=torch.empty((n, H, W, 2 * A), device=dev),
                           reg=torch.empty((n, H, W, 4 * A), device=dev),
                           info=torch.empty((n, info_cols), device=dev)) for _ in range(2)]
+        self._slot = torch.arange(post, device=dev, dtype=torch.int32)
         self.h2d_bytes = 4 * B * (H * W * (C + 6 * A) + info_cols)
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.h_out.values())
 
@@ -190,8 +247,10 @@ class HostPipeline:
                 p = self.hot.run(d["feat"][:n], d["cls"][:n], d["reg"][:n], d["info"][:n],
                                  self.need_argmax)
                 # batch indices are chunk-local on the device; make them global for the host
+                # (valid rows only: the slots behind counts[b] stay all-zero rows)
                 rois = p["rois"]
-                rois[:, 0] += float(b0)
+                valid = (self._slot[None, :] < p["counts"][:, None]).reshape(-1)
+                rois[:, 0] += valid.to(rois.dtype) * float(b0)
                 self.h_out["rois"][b0 * post:b1 * post].copy_(rois, non_blocking=True)
                 self.h_out["scores"][b0 * post:b1 * post].copy_(p["scores"], non_blocking=True)
                 self.h_out["counts"][b0:b1].copy_(p["counts"], non_blocking=True)

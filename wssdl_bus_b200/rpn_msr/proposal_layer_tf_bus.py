@@ -12,6 +12,12 @@ def _stride(feat_stride):
     return int(feat_stride[0]) if isinstance(feat_stride, (list, tuple, np.ndarray)) else int(feat_stride)
 
 
+def _nms_mode():
+    """nms_wrapper.nms (fast_rcnn/nms_wrapper.py:13-21): gpu_nms ('>' in fp32) with
+    cfg.USE_GPU_NMS, cpu_nms ('>=' against the double threshold) without."""
+    return ops.NMS_GT_F32 if cfg.USE_GPU_NMS else ops.NMS_GE_F64
+
+
 def proposal_layer(rpn_cls_prob_reshape, rpn_bbox_pred, im_info, is_training, is_ws=False,
                    _feat_stride=[16, ], anchor_scales=[8, 16, 32], return_device=False):
     """Inputs NHWC as the reference's py_func receives them: [B,H,W,2A], [B,H,W,4A], im_info
@@ -24,7 +30,7 @@ def proposal_layer(rpn_cls_prob_reshape, rpn_bbox_pred, im_info, is_training, is
     as_np = isinstance(rpn_cls_prob_reshape, np.ndarray)
     out = ops.proposals(rpn_cls_prob_reshape, rpn_bbox_pred, im_info, base, _stride(_feat_stride),
                         cfg[cfg_key].RPN_PRE_NMS_TOP_N, cfg[cfg_key].RPN_POST_NMS_TOP_N,
-                        cfg[cfg_key].RPN_NMS_THRESH, cfg[cfg_key].RPN_MIN_SIZE)
+                        cfg[cfg_key].RPN_NMS_THRESH, cfg[cfg_key].RPN_MIN_SIZE, nms_mode=_nms_mode())
     blob = ops.compact_rois(out)
     if as_np and not return_device:
         return blob.cpu().numpy()
@@ -40,7 +46,7 @@ def proposal_layer_batched(rpn_cls_prob_reshape, rpn_bbox_pred, im_info, is_trai
     return ops.proposals(rpn_cls_prob_reshape, rpn_bbox_pred, im_info, base, _stride(_feat_stride),
                          cfg[cfg_key].RPN_PRE_NMS_TOP_N, cfg[cfg_key].RPN_POST_NMS_TOP_N,
                          cfg[cfg_key].RPN_NMS_THRESH, cfg[cfg_key].RPN_MIN_SIZE,
-                         want_decoded=want_decoded)
+                         want_decoded=want_decoded, nms_mode=_nms_mode())
 
 
 def _filter_boxes(boxes, min_size):
