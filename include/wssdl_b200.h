@@ -289,7 +289,8 @@ int wssdl_anchor_labels(const float* gt_boxes, const int* num_gt, int max_gt,
  *            unused rows are zero-filled
  * pred_boxes [B*roi_stride,4K] f32 (may be NULL): the regressed + clipped boxes of :222-223
  * status     int[1] (may be NULL): 1 if some visited pair had a zero union
- * Limits: roi_stride <= 1024, K <= 64, (K-1)*roi_stride <= 1024 when cls_agnostic.
+ * Limits: roi_stride <= 1024, K <= 64, (K-1)*roi_stride <= 1024 when cls_agnostic and <= 65536
+ * otherwise (e.g. 21 classes x 300 RoIs with max_per_image = 100).
  */
 int wssdl_detect_postprocess(const float* rois, const int* roi_counts, int roi_stride,
                              const float* scores, const float* bbox_pred, const float* im_meta,

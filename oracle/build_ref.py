@@ -239,3 +239,56 @@ if __name__ == "__main__":
     print("oracle/_ref/ref_roi_pool_cudatwin.so:", "built" if ok else "reference not present; not built")
     ok = build_cuda_nms(force="--force" in sys.argv, verbose=True)
     print("oracle/_ref/ref_gpu_nms_hostbuild.so:", "built" if ok else "reference not present; not built")
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's CALL SITES of the hot path, for the drop-in test (tests/test_dropin_gpu.py).
+# Its layer modules are Python 2 sources; what travels to the GPU box (where /root/reference does
+# not exist) is their compiled form: each file is read where it lies, passed through the
+# mechanical py2 -> py3 shim (oracle/py2shim.py), compiled, and the CODE OBJECT is marshalled into
+# oracle/_ref/callsites/<name>.bin -- a build output like the .so files beside it, git-ignored.
+CALLSITES = {
+    # module name the reference imports it under -> (file, lines whose int '/' is '//' in py2)
+    "fast_rcnn.config": ("code/lib/fast_rcnn/config.py", ()),
+    "fast_rcnn.nms_wrapper": ("code/lib/fast_rcnn/nms_wrapper.py", ()),
+    "generate_anchors": ("code/lib/rpn_msr/generate_anchors.py", ()),
+    "rpn_msr.proposal_layer_tf_bus": ("code/lib/rpn_msr/proposal_layer_tf_bus.py", ()),
+    "rpn_msr.anchor_target_layer_tf_bus": ("code/lib/rpn_msr/anchor_target_layer_tf_bus.py", ()),
+    "rpn_msr.proposal_target_layer_tf_bus": ("code/lib/rpn_msr/proposal_target_layer_tf_bus.py", (57, 135)),
+}
+CALLSITES_DIR = os.path.join(OUT, "callsites")
+
+
+def callsites_built():
+    return all(os.path.isfile(os.path.join(CALLSITES_DIR, n + ".bin")) for n in CALLSITES)
+
+
+def build_callsites(force=False):
+    """Compile the reference's call-site modules into oracle/_ref/callsites/*.bin."""
+    import marshal
+    from .py2shim import py2_to_py3
+    if callsites_built() and not force:
+        return True
+    if not all(os.path.isfile(os.path.join(REF, f)) for f, _ in CALLSITES.values()):
+        return False
+    os.makedirs(CALLSITES_DIR, exist_ok=True)
+    for name, (rel, int_div) in CALLSITES.items():
+        src = py2_to_py3(open(os.path.join(REF, rel)).read(), int_div)
+        code = compile(src, "<reference>/" + rel, "exec")
+        with open(os.path.join(CALLSITES_DIR, name + ".bin"), "wb") as f:
+            marshal.dump((tuple(sys.version_info[:2]), rel, code), f)
+    return True
+
+
+def load_callsite(name):
+    """-> (relative path of the reference file, code object), or None when it was built by another
+    Python version / not built."""
+    import marshal
+    path = os.path.join(CALLSITES_DIR, name + ".bin")
+    if not os.path.isfile(path):
+        return None
+    with open(path, "rb") as f:
+        ver, rel, code = marshal.load(f)
+    if tuple(ver) != tuple(sys.version_info[:2]):
+        return None
+    return rel, code

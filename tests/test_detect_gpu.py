@@ -126,3 +126,26 @@ def test_postprocess_matches_reference_generated_golden(monkeypatch):
         want = g["det_plain_cls%d" % j]
         assert cnt[0, j] == len(want)
         np.testing.assert_allclose(dets[0, j, :cnt[0, j]], want, rtol=RTOL, atol=1e-3)
+
+
+def test_voc_sized_head_21_classes_fits(oracle_mod):
+    """21 classes x 300 RoIs with max_per_image = 100 (a VOC-sized head at the reference's
+    default settings): the per-class NMS needs mask rows for 300 boxes only; just the sort keys
+    of the cap pass cover all (K-1)*300 detections."""
+    B, S, K = 2, 300, 21
+    rois = np.concatenate([syn.rois_for_pool(70 + b, S) for b in range(B)])
+    scores, deltas = syn.rcnn_head_outputs(71, B * S, K)
+    scores = np.ascontiguousarray(scores)
+    scores[:, 1:] *= 6.0                               # enough rows above the 0.05 threshold
+    meta = np.tile(np.array([[600, 800, 1.0]], np.float32), (B, 1))
+    o = ops.detect_postprocess(rois, scores, deltas, meta, roi_stride=S, max_per_image=100,
+                               want_pred_boxes=True)
+    pb = o["pred_boxes"].cpu().numpy()
+    dets, cnt = o["dets"].cpu().numpy(), o["counts"].cpu().numpy()
+    for i in range(B):
+        want = oracle_mod.layers.detections_postprocess(scores[i * S:(i + 1) * S], pb[i * S:(i + 1) * S],
+                                                        thresh=np.float32(0.05), max_per_image=100)
+        assert sum(len(w) for w in want[1:]) <= 100 + 20
+        for j in range(1, K):
+            assert cnt[i, j] == len(want[j])
+            assert np.array_equal(dets[i, j, :cnt[i, j]], want[j])

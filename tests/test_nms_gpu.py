@@ -41,6 +41,36 @@ def test_sizes_vs_oracle(oracle_mod, n, clustered):
         assert ops.nms(d, t) == _oracle_nms(oracle_mod, d, t)
 
 
+_C5_ORACLE = {}
+
+
+def _c5_oracle(oracle_mod, n, clustered, t):
+    """cpu_nms semantics at C5 sizes: the pinned C restatement (seconds per call at 100 k);
+    cached so that the two sweep variants share one oracle run."""
+    key = (n, clustered, t)
+    if key not in _C5_ORACLE:
+        _C5_ORACLE[key] = oracle_mod.clib.nms(syn.dets(300 + n, n, clustered=clustered), t)
+    return _C5_ORACLE[key]
+
+
+@pytest.mark.parametrize("n,clustered,thresholds", [(50000, False, (0.3, 0.5, 0.7)),
+                                                    (100000, True, (0.3, 0.5, 0.7)),
+                                                    (100000, False, (0.7,))])
+def test_c5_50k_100k_keep_lists_equal_the_oracle(oracle_mod, n, clustered, thresholds, sweep_variant):
+    """BASELINE config 5 at its upper sizes, both sweeps (the cluster sweep is the default route
+    from N = 65536): keep lists bit-exact against cpu_nms semantics."""
+    d = syn.dets(300 + n, n, clustered=clustered)
+    for t in thresholds:
+        assert ops.nms(d, t) == _c5_oracle(oracle_mod, n, clustered, t), (n, clustered, t, sweep_variant)
+
+
+def test_c5_default_route_is_the_cluster_sweep_from_65536(oracle_mod, tuning):
+    """Without a forced variant: N = 100 k takes the cluster sweep, and gives the oracle's list."""
+    tuning("nms_sweep_cluster", -1)
+    d = syn.dets(300 + 100000, 100000, clustered=True)
+    assert ops.nms(d, 0.5) == _c5_oracle(oracle_mod, 100000, True, 0.5)
+
+
 def test_c5_sweep_large_properties(oracle_mod):
     """N = 20k / 50k / 100k: oracle at 20k (C restatement, seconds); beyond that properties:
     keep sorted by score, no kept pair above the threshold, every dropped box has a kept

@@ -402,18 +402,19 @@ extern "C" int wssdl_detect_postprocess(const float* rois, const int* roi_counts
   a.B = B; a.K = K; a.score_thresh = score_thresh;
   a.nms = make_thresh(nms_thresh, WSSDL_NMS_GE_F64);
   a.max_per_image = max_per_image; a.cls_agnostic = cls_agnostic ? 1 : 0;
-  // the class-agnostic pass and the cap see up to (K-1)*S detections at once
-  const long long nmax = (cls_agnostic || max_per_image > 0) ? (long long)(K - 1) * roi_stride
-                                                               : (long long)roi_stride;
-  if (roi_stride > DET_MAX_N || (cls_agnostic && nmax > DET_MAX_N)) return WSSDL_ELIMIT;
-  a.nmax = (int)nmax;
+  // One NMS problem at a time lives in shared memory: a class (<= S boxes) or, class-agnostic,
+  // all classes together (<= (K-1)*S).  Boxes, scores and mask rows are sized for that; only the
+  // sort keys also serve the max_per_image cap, which ranks up to (K-1)*S scores.
+  const long long all = (long long)(K - 1) * roi_stride;
+  const long long nms_n = cls_agnostic ? all : (long long)roi_stride;
+  if (roi_stride > DET_MAX_N || nms_n > DET_MAX_N) return WSSDL_ELIMIT;
+  a.nmax = (int)nms_n;
+  const long long nkeys = (cls_agnostic || max_per_image > 0) ? all : (long long)roi_stride;
+  if (nkeys > (1 << 16)) return WSSDL_ELIMIT;
   a.NP = 1;
-  while (a.NP < a.nmax) a.NP <<= 1;
-  // the mask only ever covers one NMS problem: per class (<= S boxes) or agnostic (<= nmax)
-  const int nms_n = cls_agnostic ? a.nmax : roi_stride;
-  a.nblk = (nms_n + 63) / 64;
+  while (a.NP < nkeys) a.NP <<= 1;
+  a.nblk = (int)((nms_n + 63) / 64);
   a.dets = dets; a.det_counts = det_counts; a.pred_boxes = pred_boxes; a.status = status;
-  // mask rows are only needed for nms_n boxes; the other arrays for nmax
   const size_t smem = det_smem_bytes(a.nmax, a.NP, a.nblk);
   if (smem > 227 * 1024 - 1024) return WSSDL_ELIMIT;
   static unsigned long long done = 0;

@@ -171,6 +171,7 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blo
   extern __shared__ unsigned long long remv[];   // col_blocks words
   __shared__ unsigned long long s_kept[2];       // kept mask of block b at [b & 1]
   __shared__ int s_count;
+  __shared__ int s_full[2];          // [b & 1]: the keep list is full after block b
   __shared__ int s_rows[2][64];                  // kept rows of block b at [b & 1]
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < col_blocks; i += SWEEP_THREADS) remv[i] = 0;
@@ -246,7 +247,11 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blo
       if ((K >> (lane + 32)) & 1ull)
         s_rows[b & 1][__popcll(K & ((1ull << (lane + 32)) - 1ull))] = lane + 32;
       __syncwarp();                       // every lane has read s_count (racecheck: WAR)
-      if (lane == 0) { s_kept[b & 1] = K; s_count = count + take; }
+      if (lane == 0) {
+        s_kept[b & 1] = K;
+        s_count = count + take;
+        s_full[b & 1] = count + take >= limit;
+      }
     } else if (b > 0) {
       // ---- OR the kept rows of block b-1 into the removal bitmap of column blocks >= b+1
       // (column b was handled by warp 0's `fast`).  (kept row, column) pairs are spread over
@@ -290,7 +295,9 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, int N, int col_blo
       }
     }
     __syncthreads();
-    if (s_count >= limit) break;
+    // read a slot warp 0 will not touch again before every warp has passed the NEXT barrier
+    // (s_count itself is rewritten by warp 0 as soon as it runs ahead into block b + 1)
+    if (s_full[b & 1]) break;
   }
   if (tid == 0) *num_keep = s_count;
 }

@@ -16,6 +16,7 @@ struct Thresh {
   float gt;       // mode GT_F32: (float)thresh, test is '>'
   int use_gt;
   int contain;    // nms_new's extra containment tests
+  float eff;      // either mode as ONE test: suppressed iff iou >= eff (x > gt  <=>  x >= next float up)
 };
 
 // max/min exactly as cpu_nms.pyx:11-15 (NaN-asymmetric like the reference)
@@ -34,14 +35,14 @@ __device__ __forceinline__ bool suppresses(const float4 bi, float ai, const floa
   const float inter = __fmul_rn(w, h);
   const float den = __fsub_rn(__fadd_rn(ai, aj), inter);
   if (den == 0.0f) *zero = true;
-  const float ovr = iou_quotient(inter, den);
-  bool s = th.use_gt ? (ovr > th.gt) : (ovr >= th.ge);
+  // (the IEEE division only where the quotient is within 2^-19 of the threshold: common.cuh)
+  bool s = iou_ge_exact(inter, den, th.eff);
   if (th.contain) {
     // nms.pyx:117-120: float division, compared against the double 0.95: x > 0.95 for a float x
-    // is x > 0.949999988f (the largest float below 0.95), i.e. x >= 0.95000005f
-    const float c95 = 0.949999988079071044921875f;
+    // is x > 0.949999988f (the largest float below 0.95), i.e. x >= 0.95000005f, the next float
+    const float c95 = 0.95000004768371582031f;
     if (ai == 0.0f || aj == 0.0f) *zero = true;   // the reference raises there as well
-    s = s || (iou_quotient(inter, ai) > c95) || (iou_quotient(inter, aj) > c95);
+    s = s || iou_ge_exact(inter, ai, c95) || iou_ge_exact(inter, aj, c95);
   }
   return s;
 }
@@ -55,6 +56,7 @@ inline Thresh make_thresh(double thresh, int mode) {
   float f = (float)thresh;
   if ((double)f < thresh) f = nextafterf(f, INFINITY);
   t.ge = f;
+  t.eff = t.use_gt ? nextafterf(t.gt, INFINITY) : t.ge;
   return t;
 }
 

@@ -8,9 +8,9 @@
 //   cpu_nms (nms/cpu_nms.pyx:17-68) -> post-NMS top-N (:139-146) -> (R,5) blob.
 //
 // Phases of the kernel (1024 threads, one image):
-//   1. decode+clip+filter every anchor; keep only a 32-bit orderable score key per anchor
-//      in shared memory (0 = filtered out).  Boxes are NOT stored: they are a pure
-//      function of (anchor index, 4 deltas) and are recomputed bit-identically when needed.
+//   1. a 32-bit orderable score key per anchor in shared memory.  Boxes are NOT stored: they are
+//      a pure function of (anchor index, 4 deltas) and are decoded (+clipped, +min-size filtered)
+//      bit-identically whenever needed -- lazily, for the candidates of a batch only.
 //   2./3. the K = min(pre_nms_topN, #valid) best anchors in the reference's order (score desc,
 //      index desc for ties) are produced LAZILY, M at a time: a radix select (4 x 8-bit
 //      histogram passes over the shared keys, a second select on the anchor index for ties at
@@ -119,7 +119,7 @@ __device__ __forceinline__ bool iou_ge(const float4 bi, float ai, const float4 b
   const float h = rmax(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
   const float inter = __fmul_rn(w, h);
   const float den = __fsub_rn(__fadd_rn(ai, aj), inter);
-  return iou_quotient(inter, den) >= thr_ge;
+  return iou_ge_exact(inter, den, thr_ge);
 }
 
 // K-th largest (1-based) among n keys in shared memory, considering only keys accepted by
@@ -193,6 +193,7 @@ proposals_kernel(const PropParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned s_xchg[2][CS][XCHG_WORDS];    // [slot set][source CTA][word]
   __shared__ unsigned s_sup[XCHG_WORDS];            // this CTA's partial "suppressed" bitmap
+  __shared__ int s_wcnt[PT / 32];                   // per-warp counts of a block-wide compaction
   namespace cg = cooperative_groups;
   int crank = 0;
   if constexpr (CS > 1) {
@@ -227,39 +228,34 @@ proposals_kernel(const PropParams p) {
   const float min_size = __fmul_rn(p.min_size, info[2]);    // :123, fp32 product
   const int post = p.post_nms_topN;
 
-  // ---- phase 1: decode, clip, filter -> keys
-  if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
-  __syncthreads();
-  int my_valid = 0;
+  // ---- phase 1: a score key for EVERY anchor.  The min-size filter (:123) is applied lazily,
+  // to the candidates of a batch: walking the anchors in score order and skipping the boxes that
+  // fail the filter visits the same sequence as filtering first and sorting the rest, so only a
+  // few hundred of the 17100 boxes are ever decoded (the full decode was 24 % of the kernel).
+  if (tid == 0) s_cnt[1] = 0;
   for (int a = tid; a < p.NA; a += PT) {
-    const float4 b = decode_anchor(p, img, a, im_h, im_w);
-    if (p.decoded && writer) reinterpret_cast<float4*>(p.decoded)[(size_t)img * p.NA + a] = b;
-    const float ws = __fadd_rn(__fsub_rn(b.z, b.x), 1.0f);
-    const float hs = __fadd_rn(__fsub_rn(b.w, b.y), 1.0f);
-    const bool ok = (ws >= min_size) && (hs >= min_size);
     const int cell = a / p.A;
     const int an = a - cell * p.A;
     const float sc = __ldg(p.cls_prob + ((size_t)img * p.H * p.W + cell) * (2 * p.A) + p.A + an);
-    s_keys[a] = ok ? orderable_key(sc) : 0u;
-    my_valid += ok ? 1 : 0;
+    s_keys[a] = orderable_key(sc);
+    if (p.decoded && writer)                  // the intermediate of :116-119, only when asked for
+      reinterpret_cast<float4*>(p.decoded)[(size_t)img * p.NA + a] = decode_anchor(p, img, a, im_h, im_w);
   }
-  my_valid = __reduce_add_sync(0xffffffffu, my_valid);
-  if (lane == 0 && my_valid) atomicAdd(&s_cnt[0], my_valid);
   __syncthreads();
-  const int n_valid = s_cnt[0];
-  const int K = min(p.pre_nms_topN, n_valid);
 
-  // ---- phases 2-4: batches of M candidates in descending order, keep-list NMS over each
+  // ---- phases 2-4: batches of M anchors in descending score order; decode + filter the batch;
+  // keep-list NMS over its valid boxes
   const int M = p.kpad;
   int nkept = 0;
   int round = 0;
+  int taken_valid = 0;                        // valid candidates consumed so far (<= pre_nms_topN)
   unsigned Tp = 0, T2p = 0;                   // boundary behind the previous batch
-  for (int taken = 0; taken < K && nkept < post; taken += M) {
-    const int want = min(taken + M, K);       // rank of the last candidate of this batch
-    // boundary (T, T2): candidate (k, a) is among the best `want` iff k > T or (k == T and
+  for (int taken = 0; taken < p.NA && taken_valid < p.pre_nms_topN && nkept < post; taken += M) {
+    const int want = min(taken + M, p.NA);    // rank of the last anchor of this batch
+    // boundary (T, T2): anchor (k, a) is among the best `want` iff k > T or (k == T and
     // a + 1 >= T2): key and, among ties at T, the highest indices first
     unsigned T = 0, T2 = 0;
-    if (want < n_valid) {
+    if (want < p.NA) {
       int n_gt = 0;
       T = radix_select([&](int i) { return s_keys[i]; }, p.NA, want, s_hist, s_bcast, &n_gt);
       const int need_eq = want - n_gt;        // how many keys == T are in (highest indices)
@@ -273,7 +269,7 @@ proposals_kernel(const PropParams p) {
     __syncthreads();
     for (int a = tid; a < p.NA; a += PT) {
       const unsigned k = s_keys[a];
-      const bool in_now = (k != 0u) && (k > T || (k == T && (unsigned)(a + 1) >= T2));
+      const bool in_now = k > T || (k == T && (unsigned)(a + 1) >= T2);
       const bool in_before = taken > 0 && (k > Tp || (k == Tp && (unsigned)(a + 1) >= T2p));
       if (in_now && !in_before) {
         const int pos = atomicAdd(&s_cnt[1], 1);
@@ -294,7 +290,37 @@ proposals_kernel(const PropParams p) {
     }
     Tp = T;
     T2p = T2;
-    const int nbatch = want - taken;
+    // decode + min-size filter (:123, :151-156), order-preserving compaction in place (an entry
+    // only ever moves towards the front, and a block of PT entries is read before it is written)
+    int nvalid = 0;
+    for (int base = 0; base < want - taken; base += PT) {
+      const int i = base + tid;
+      unsigned long long e = 0;
+      bool ok = false;
+      if (i < want - taken) {
+        e = s_sort[i];
+        const int a = (int)(~(unsigned)(e & 0xffffffffull));
+        const float4 bx = decode_anchor(p, img, a, im_h, im_w);
+        const float ws = __fadd_rn(__fsub_rn(bx.z, bx.x), 1.0f);
+        const float hs = __fadd_rn(__fsub_rn(bx.w, bx.y), 1.0f);
+        ok = (ws >= min_size) && (hs >= min_size);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) s_wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < PT / 32; ++w) {
+        const int c = s_wcnt[w];
+        if (w < warp) before += c;
+        total += c;
+      }
+      if (ok) s_sort[nvalid + before + __popc(bal & ((1u << lane) - 1u))] = e;
+      nvalid += total;
+      __syncthreads();
+    }
+    const int nbatch = min(nvalid, p.pre_nms_topN - taken_valid);   // :130-131
+    taken_valid += nvalid;
   for (int c0 = 0; c0 < nbatch && nkept < post; c0 += CHUNK, ++round) {
     const int nc = min(CHUNK, nbatch - c0);
     if (tid < CHUNK) {
