@@ -269,6 +269,89 @@ int wssdl_anchor_labels(const float* gt_boxes, const int* num_gt, int max_gt,
                         double* max_overlap, void* workspace, size_t workspace_bytes,
                         wssdl_stream_t stream);
 
+/* ---------------------------------------------------------------- anchor targets (sampled part)
+ * Replaces the rest of anchor_target_layer[_joint] (rpn_msr/anchor_target_layer_tf_bus.py:
+ * 512-611): fg / bg subsampling, regression targets (:533 -> fast_rcnn/bbox_transform.py:10-28
+ * with the reference's dtypes: float64 anchors, float32 GT rows, one cast to float32), inside /
+ * outside weights, `_unmap` and the final layouts, for the whole batch in one launch fed by
+ * wssdl_anchor_labels -- nothing returns to the host in between.
+ *
+ * labels_pre, argmax_gt  [B_supervised, H*W*A] as written by wssdl_anchor_labels
+ * gt_boxes   [B_supervised, max_gt, 5] f32 (the same tensor)
+ * B_total >= B_supervised: the images behind the supervised ones are weakly supervised and get
+ *            labels -1, zero targets and weights (:613-626)
+ * num_fg = int(RPN_FG_FRACTION * RPN_BATCHSIZE), batchsize = RPN_BATCHSIZE (:513, :523)
+ * sample_mode WSSDL_SAMPLE_RANKS: the caller drew with the host RNG (the reference's stream);
+ *            `ranks` (device) holds, image after image, the ranks of the fg anchors to disable and
+ *            then those of the bg anchors (rank = position among the image's anchors of that label
+ *            in ascending index order -- what npr.choice(len, size, replace=False) returns),
+ *            rank_off [2*B_supervised+1] (device) their offsets; the population sizes come from
+ *            wssdl_anchor_label_counts (counts [B,2] = fg, bg);
+ *            WSSDL_SAMPLE_PHILOX: drawn on the device, no host trip: anchor i of image b has the
+ *            key philox4x32-10(counter (i, b, which, 0), key seed).x, which = 0 fg / 1 bg; the
+ *            anchors with the smallest (key, i) are disabled.
+ * inside_weights [4] f32 HOST (RPN_BBOX_INSIDE_WEIGHTS); positive_weight = RPN_POSITIVE_WEIGHT
+ *            (< 0: uniform 1 / #examples, :541-545)
+ * labels_out [B_total,1,A*H,W] f32; targets, inside, outside [B_total,4A,H,W] f32 (:568-598)
+ * final_counts [B_supervised,2] i32 (may be NULL): fg, bg after subsampling
+ * Limits: A <= 32, H*W*A <= 32768.
+ */
+enum { WSSDL_SAMPLE_RANKS = 0, WSSDL_SAMPLE_PHILOX = 1 };
+
+int wssdl_anchor_label_counts(const float* labels, int B, int NA, int* counts,
+                              wssdl_stream_t stream);
+
+int wssdl_anchor_targets(const float* labels_pre, const int* argmax_gt, const float* gt_boxes,
+                         int max_gt, int B_supervised, int B_total, int H, int W, int A,
+                         const float* base_anchors, int feat_stride, int num_fg, int batchsize,
+                         int sample_mode, const int* ranks, const int* rank_off,
+                         unsigned long long seed, const float* inside_weights,
+                         double positive_weight, float* labels_out, float* targets, float* inside,
+                         float* outside, int* final_counts, wssdl_stream_t stream);
+
+/* ---------------------------------------------------------------- proposal targets, on device
+ * Replaces proposal_target_layer / proposal_target_layer_joint for the supervised images
+ * (rpn_msr/proposal_target_layer_tf_bus.py:15-184) and _sample_rois (:228-280),
+ * _compute_targets (:213-226), _get_bbox_regression_labels (:187-210).  Two launches:
+ *
+ * wssdl_roi_match   per image i < B_supervised: the candidates are the rows of `rois` whose batch
+ *            column is i, in their original order, followed -- when add_gt -- by the image's fg GT
+ *            rows (the leading rows of gt_boxes[i,:num_gt[i]] with class != 0, :38-50); fp64 IoU as
+ *            utils/bbox.pyx:15-55, max / first argmax (:233-235), fg candidacy max >= fg_thresh
+ *            (:239), bg candidacy bg_thresh_lo <= max < bg_thresh_hi (:252-253).
+ *            counts [B_supervised,4] i32 = (candidates, fg candidates, bg candidates, fg GT rows).
+ *            The candidate table stays in `workspace` for wssdl_roi_targets.
+ * wssdl_roi_targets  the selected candidates into output rows: RoI (GT candidates as (i, box)),
+ *            label (class of the assigned GT; 0 from row fg_this on, :264-266), fp32 bbox_transform
+ *            targets, normalised in fp64 when the two double[4] arrays are given (:221-224),
+ *            expanded to [.,4*num_classes] with inside / outside (= inside > 0, :84) weights.
+ *   WSSDL_SAMPLE_RANKS   sel holds, per image, the fg then the bg selection as RANKS among the
+ *            fg / bg candidates, in selection order -- what npr.choice(n, size=k, replace=False)
+ *            returns for a population of that size; sel_off [2*B_supervised+1] delimits them and
+ *            row_off [B_supervised+1] is the first output row of every image (no padding).
+ *   WSSDL_SAMPLE_PHILOX  fg_this = min(fg_rois_per_image, n_fg), bg_this = min(rois_per_image -
+ *            fg_this, n_bg) (:243, :256-258); the fg_this (bg_this) candidates with the smallest
+ *            (philox4x32-10(counter (rank, i, 2 fg / 3 bg, 0), key seed).x, rank), in that order.
+ *            Image i owns output rows [i*rois_per_image, (i+1)*rois_per_image); rows past
+ *            fg_this + bg_this are zero; out_counts [B_supervised,2] = (fg_this, bg_this).
+ * Limits: max_gt <= 64; 2*(R+max_gt) (+ rois_per_image + R + max_gt with Philox) ints of shared
+ * memory <= 200 KB, else WSSDL_ELIMIT. */
+size_t wssdl_roi_targets_workspace_bytes(int B_supervised, int R, int max_gt);
+
+int wssdl_roi_match(const float* rois, int R, const float* gt_boxes, const int* num_gt,
+                    int max_gt, int B_supervised, int add_gt, double fg_thresh,
+                    double bg_thresh_hi, double bg_thresh_lo, void* workspace,
+                    size_t workspace_bytes, int* counts, wssdl_stream_t stream);
+
+int wssdl_roi_targets(const float* rois, int R, const float* gt_boxes, int max_gt,
+                      int B_supervised, int num_classes, const void* workspace, const int* counts,
+                      int sample_mode, const int* sel, const int* sel_off, const int* row_off,
+                      int fg_rois_per_image, int rois_per_image, unsigned long long seed,
+                      const double* normalize_means, const double* normalize_stds,
+                      const float* inside_weights, float* out_rois, float* out_labels,
+                      float* out_targets, float* out_inside, float* out_outside, int* out_counts,
+                      wssdl_stream_t stream);
+
 /* ---------------------------------------------------------------- detection post-processing
  * Replaces the tail of im_detect (fast_rcnn/test_bus.py:207-223: rois / im_scale,
  * bbox_transform_inv per class, _clip_boxes :124-134) and the per-image body of test_net

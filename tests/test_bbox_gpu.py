@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from wssdl_bus_b200 import ops, synthetic as syn
+from wssdl_bus_b200.rpn_msr.generate_anchors import generate_anchors
 
 pytestmark = pytest.mark.gpu
 
@@ -169,3 +170,111 @@ def test_target_layers_match_reference_generated_golden(monkeypatch):
     assert blob.shape == g["prop_blob_test"].shape
     np.testing.assert_allclose(blob, g["prop_blob_test"], rtol=RTOL, atol=1e-3)
     del names
+
+
+def test_anchor_targets_device_sampler_philox(oracle_mod):
+    """sampler="philox": the subsampling is drawn on the device (no host trip).  The draw differs
+    from numpy's, so the check is structural: quotas met exactly, survivors are a subset of the
+    pre-subsample labels, targets and inside weights independent of the sampler, outside weights
+    1 / #examples, deterministic per seed, different across seeds and images; device tensors in ->
+    device tensors out."""
+    import torch
+    from wssdl_bus_b200.fast_rcnn.config import cfg
+    from wssdl_bus_b200.rpn_msr import anchor_target_layer_tf_bus as atl
+    H, W, A, B = 38, 50, 9, 3
+    gt, num = syn.gt_boxes(520, B)
+    gt[1, 2] = [10, 10, 780, 590, 0]                     # a huge explicit background box: many bg anchors
+    num[1] = max(num[1], 3)
+    info = np.tile(np.array([[600, 800, 1.0]], np.float32), (B, 1))
+    score = np.zeros((B, H, W, 2 * A), np.float32)
+    np.random.seed(11)
+    host = atl.anchor_target_layer(score, gt, num, info, None, [16, ], [8, 16, 32], "VOC")
+    dev = atl.anchor_target_layer(score, torch.from_numpy(gt).cuda(), torch.from_numpy(num).cuda(),
+                                  torch.from_numpy(info).cuda(), None, [16, ], [8, 16, 32], "VOC",
+                                  sampler="philox", seed=1234)
+    assert all(torch.is_tensor(t) and t.is_cuda for t in dev)
+    lab, tgt, iw, ow = [t.cpu().numpy() for t in dev]
+    again = atl.anchor_target_layer(score, gt, num, info, None, [16, ], [8, 16, 32], "VOC",
+                                    sampler="philox", seed=1234)
+    other = atl.anchor_target_layer(score, gt, num, info, None, [16, ], [8, 16, 32], "VOC",
+                                    sampler="philox", seed=99)
+    assert all(np.array_equal(a, b) for a, b in zip((lab, tgt, iw, ow), again))
+    assert not np.array_equal(lab, other[0])
+    assert np.array_equal(tgt, host[1])                   # targets do not depend on the draws
+    num_fg = int(cfg.TRAIN.RPN_FG_FRACTION * cfg.TRAIN.RPN_BATCHSIZE)
+    labels_pre, _, _ = ops.anchor_labels(gt, num, info, H, W, generate_anchors(), 16, dataset_mode=2,
+                                         positive_overlap=cfg.TRAIN.RPN_POSITIVE_OVERLAP,
+                                         negative_overlap=cfg.TRAIN.RPN_NEGATIVE_OVERLAP,
+                                         clobber_positives=cfg.TRAIN.RPN_CLOBBER_POSITIVES)
+    pre = labels_pre.cpu().numpy().reshape(B, H, W, A).transpose(0, 3, 1, 2).reshape(B, 1, A * H, W)
+    drew = 0
+    for b in range(B):
+        n_fg, n_bg = int((pre[b] == 1).sum()), int((pre[b] == 0).sum())
+        fg, bg = int((lab[b] == 1).sum()), int((lab[b] == 0).sum())
+        assert fg == min(n_fg, num_fg) and bg == min(n_bg, cfg.TRAIN.RPN_BATCHSIZE - fg)
+        assert np.all(pre[b][lab[b] == 1] == 1) and np.all(pre[b][lab[b] == 0] == 0)
+        drew += (n_fg > fg) + (n_bg > bg)
+        lab4 = np.repeat(lab[b].reshape(A, H, W), 4, axis=0)
+        assert np.array_equal(iw[b] != 0, lab4 == 1)
+        assert np.array_equal(ow[b][lab4 >= 0], np.full(int((lab4 >= 0).sum()), np.float32(1.0 / (fg + bg))))
+        assert not ow[b][lab4 < 0].any()
+    assert drew >= 2                                      # the sampler actually had to draw
+    assert not np.array_equal(lab[0], lab[2]) or not np.array_equal(pre[0], pre[2])
+
+
+def test_proposal_targets_device_sampler_philox(oracle_mod):
+    """sampler="philox" for the proposal-target layer: fixed row stride, no host trip.  Structural
+    checks against the oracle's candidate sets: the fg rows are distinct fg candidates, the bg rows
+    distinct bg candidates, quotas as :243 / :256-258, labels / targets / weights of every row
+    what the oracle computes for that row; deterministic per seed, different across seeds."""
+    import torch
+    from wssdl_bus_b200.fast_rcnn.config import cfg
+    from wssdl_bus_b200.rpn_msr import proposal_target_layer_tf_bus as ptl
+    B, K = 3, 3
+    gt, num = syn.gt_boxes(530, B)
+    rois = np.concatenate([np.hstack((np.full((300 + 50 * i, 1), i, np.float32),
+                                      syn.rois_for_pool(531 + i, 300 + 50 * i)[:, 1:])) for i in range(B)])
+    rois = rois[np.random.RandomState(5).permutation(len(rois))]        # interleaved images
+    dev = torch.device("cuda:0")
+    out = ptl.proposal_target_layer(torch.from_numpy(rois).to(dev), torch.from_numpy(gt).to(dev),
+                                    torch.from_numpy(num.astype(np.int32)).to(dev), K, True, False,
+                                    sampler="philox", seed=9)
+    r, l, t, iw, ow, cnt = out
+    assert all(x.is_cuda for x in out)
+    S = cfg.TRAIN.BATCH_SIZE
+    fgq = int(np.round(cfg.TRAIN.FG_FRACTION * S))
+    assert r.shape == (B * S, 5) and l.shape == (B * S, 1) and t.shape == (B * S, 4 * K)
+    r, l, t, iw, ow, cnt = (x.cpu().numpy() for x in out)
+    for i in range(B):
+        pos = gt[i, :int((gt[i, :num[i], 4] != 0).sum())]
+        allr = np.vstack((rois[rois[:, 0] == i], np.hstack((np.full((len(pos), 1), i, np.float32), pos[:, :4]))))
+        ov = oracle_mod.clib.bbox_overlaps(allr[:, 1:5].astype(np.float64), pos[:, :4].astype(np.float64))
+        mx, am = ov.max(axis=1), ov.argmax(axis=1)
+        fg = np.where(mx >= cfg.TRAIN.FG_THRESH)[0]
+        bg = np.where((mx < cfg.TRAIN.BG_THRESH_HI) & (mx >= cfg.TRAIN.BG_THRESH_LO))[0]
+        nf, nb = min(fgq, fg.size), min(S - min(fgq, fg.size), bg.size)
+        assert tuple(cnt[i]) == (nf, nb)
+        rows = r[i * S:i * S + nf + nb]
+        key = {tuple(v): j for j, v in enumerate(map(tuple, allr))}
+        idx = np.array([key[tuple(v)] for v in rows])
+        assert len(set(idx[:nf])) == nf and set(idx[:nf]) <= set(fg)
+        assert len(set(idx[nf:])) == nb and set(idx[nf:]) <= set(bg)
+        want_l = pos[am[idx], 4].copy()
+        want_l[nf:] = 0
+        assert np.array_equal(l[i * S:i * S + nf + nb, 0], want_l)
+        tg = oracle_mod.layers.bbox_transform(rows[:, 1:5], pos[am[idx], :4])
+        if cfg.TRAIN.BBOX_NORMALIZE_TARGETS_PRECOMPUTED:
+            tg = (tg - np.array(cfg.TRAIN.BBOX_NORMALIZE_MEANS)) / np.array(cfg.TRAIN.BBOX_NORMALIZE_STDS)
+        for j in range(nf + nb):
+            c = int(want_l[j])
+            row_t, row_i = t[i * S + j].reshape(K, 4), iw[i * S + j].reshape(K, 4)
+            if c > 0:
+                np.testing.assert_allclose(row_t[c], tg[j], rtol=RTOL, atol=1e-6)
+                assert np.array_equal(row_i[c], np.asarray(cfg.TRAIN.BBOX_INSIDE_WEIGHTS, np.float32))
+            assert not row_t[[k for k in range(K) if k != c or c == 0]].any()
+        assert np.array_equal(ow, (iw > 0).astype(np.float32))
+        assert not r[i * S + nf + nb:(i + 1) * S].any() and not t[i * S + nf + nb:(i + 1) * S].any()
+    again = ptl.proposal_target_layer(rois, gt, num, K, True, False, sampler="philox", seed=9)
+    assert np.array_equal(again[0], r) and np.array_equal(again[2], t)
+    other = ptl.proposal_target_layer(rois, gt, num, K, True, False, sampler="philox", seed=10)
+    assert not np.array_equal(other[0], r)

@@ -17,6 +17,7 @@ BIN_CPU_TRUNC, BIN_GPU_CEIL = 0, 1
 BWD_ATOMIC, BWD_GATHER = 0, 1
 NMS_GE_F64, NMS_GT_F32, NMS_CONTAIN = 0, 1, 4
 IOU, IOU_UI = 0, 1
+SAMPLE_RANKS, SAMPLE_PHILOX = 0, 1
 
 _vp, _i, _f, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t
 
@@ -48,6 +49,13 @@ SIGNATURES = {
     "wssdl_eval_match": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _d, _f, _vp, _vp, _vp, _vp, _vp,
                               _vp]),
     "wssdl_anchor_labels_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "wssdl_anchor_label_counts": (_i, [_vp, _i, _i, _vp, _vp]),
+    "wssdl_anchor_targets": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp,
+                                  ctypes.c_ulonglong, _vp, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wssdl_roi_targets_workspace_bytes": (_sz, [_i, _i, _i]),
+    "wssdl_roi_match": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d, _vp, _sz, _vp, _vp]),
+    "wssdl_roi_targets": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i,
+                               ctypes.c_ulonglong, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wssdl_anchor_labels": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _d, _d, _i,
                                  _vp, _vp, _vp, _vp, _sz, _vp]),
 }

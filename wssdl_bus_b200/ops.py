@@ -426,6 +426,155 @@ def anchor_labels(gt_boxes, num_gt, im_info, H, W, base_anchors, feat_stride, da
     return labels, argmax, maxov
 
 
+def anchor_label_counts(labels):
+    """labels [B,NA] f32 (as written by anchor_labels) -> counts [B,2] i32 on the device:
+    fg (== 1) and bg (== 0) anchors per image: the population sizes the host RNG needs to draw
+    the reference's npr.choice subsamples (anchor_target_layer_tf_bus.py:514, :524)."""
+    labels = _cuda(labels, torch.float32)
+    B, NA = labels.shape
+    with torch.cuda.device(labels.device):
+        counts = torch.empty((B, 2), dtype=torch.int32, device=labels.device)
+        rc = _lib.lib().wssdl_anchor_label_counts(_ptr(labels), B, NA, _ptr(counts),
+                                                  _stream(labels.device))
+    _lib.check(rc, "wssdl_anchor_label_counts")
+    return counts
+
+
+def anchor_targets(labels_pre, argmax_gt, gt_boxes, B_total, H, W, base_anchors, feat_stride, num_fg,
+                   batchsize, inside_weights=(1.0, 1.0, 1.0, 1.0), positive_weight=-1.0, ranks=None,
+                   rank_off=None, seed=None):
+    """Sampled part of anchor_target_layer[_joint] on the device (csrc/targets.cu): subsampling,
+    fp64 regression targets, weights, `_unmap` and the final layouts for the whole batch.
+
+    labels_pre / argmax_gt [Bs,NA], gt_boxes [Bs,max_gt,5]: outputs / input of anchor_labels.
+    Sampling: ranks + rank_off (host-drawn disable ranks: the parity mode) or seed (Philox on
+    the device, no host trip).  Returns device tensors (labels [B_total,1,A*H,W], targets, inside,
+    outside [B_total,4A,H,W], final_counts [Bs,2] i32)."""
+    labels_pre = _cuda(labels_pre, torch.float32)
+    dev = labels_pre.device
+    argmax_gt = _cuda(argmax_gt, torch.int32, dev)
+    gt_boxes = _cuda(gt_boxes, torch.float32, dev)
+    base = np.ascontiguousarray(base_anchors, dtype=np.float32)
+    A = base.shape[0]
+    Bs = labels_pre.shape[0]
+    NA = H * W * A
+    if Bs and (tuple(labels_pre.shape) != (Bs, NA) or tuple(argmax_gt.shape) != (Bs, NA) or
+               gt_boxes.dim() != 3 or gt_boxes.shape[0] != Bs or gt_boxes.shape[2] != 5):
+        raise ValueError("labels_pre / argmax_gt [Bs,H*W*A], gt_boxes [Bs,max_gt,5]")
+    if (ranks is None) == (seed is None):
+        raise ValueError("pass either host-drawn ranks (+ rank_off) or a Philox seed")
+    iw = np.ascontiguousarray(inside_weights, dtype=np.float32)
+    with torch.cuda.device(dev):
+        if ranks is not None:
+            mode = _lib.SAMPLE_RANKS
+            ranks = _cuda(np.asarray(ranks, dtype=np.int32) if not torch.is_tensor(ranks) else ranks,
+                          torch.int32, dev)
+            rank_off = _cuda(np.asarray(rank_off, dtype=np.int32) if not torch.is_tensor(rank_off)
+                             else rank_off, torch.int32, dev)
+            if rank_off.numel() != 2 * Bs + 1:
+                raise ValueError("rank_off must hold 2*Bs+1 offsets")
+        else:
+            mode = _lib.SAMPLE_PHILOX
+        labels = torch.empty((B_total, 1, A * H, W), dtype=torch.float32, device=dev)
+        targets = torch.empty((B_total, 4 * A, H, W), dtype=torch.float32, device=dev)
+        inside = torch.empty_like(targets)
+        outside = torch.empty_like(targets)
+        fc = torch.empty((max(Bs, 1), 2), dtype=torch.int32, device=dev)
+        rc = _lib.lib().wssdl_anchor_targets(
+            _ptr(labels_pre), _ptr(argmax_gt), _ptr(gt_boxes), max(int(gt_boxes.shape[1]), 1) if Bs else 1,
+            Bs, int(B_total), H, W, A, base.ctypes.data_as(_vp), int(feat_stride), int(num_fg),
+            int(batchsize), mode, _ptr(ranks), _ptr(rank_off), int(seed or 0) & (2 ** 64 - 1),
+            iw.ctypes.data_as(_vp), float(positive_weight), _ptr(labels), _ptr(targets), _ptr(inside),
+            _ptr(outside), _ptr(fc), _stream(dev))
+    _lib.check(rc, "wssdl_anchor_targets")
+    return labels, targets, inside, outside, fc[:Bs]
+
+
+class RoiMatch(object):
+    """Candidate table of roi_match (kept on the device for roi_targets)."""
+    __slots__ = ("rois", "gt_boxes", "workspace", "counts", "n_supervised")
+
+    def __init__(self, rois, gt_boxes, workspace, counts, n_supervised):
+        self.rois, self.gt_boxes, self.workspace = rois, gt_boxes, workspace
+        self.counts, self.n_supervised = counts, n_supervised
+
+
+def roi_match(rois, gt_boxes, num_gt, add_gt, fg_thresh, bg_thresh_hi, bg_thresh_lo):
+    """First half of _sample_rois for every supervised image (csrc/targets.cu roi_match_kernel):
+    candidates = the image's RoIs (+ its fg GT rows when add_gt), fp64 IoU, max / argmax, fg / bg
+    candidacy and ranks.  rois [R,5], gt_boxes [Bs,max_gt,5], num_gt [Bs].  Returns a RoiMatch whose
+    .counts [Bs,4] i32 = (candidates, fg candidates, bg candidates, fg GT rows)."""
+    gt_boxes = _cuda(gt_boxes, torch.float32)
+    dev = gt_boxes.device
+    rois = _cuda(rois, torch.float32, dev)
+    num_gt = _cuda(num_gt, torch.int32, dev)
+    if rois.dim() != 2 or rois.shape[1] != 5 or gt_boxes.dim() != 3 or gt_boxes.shape[2] != 5:
+        raise ValueError("rois [R,5], gt_boxes [Bs,max_gt,5]")
+    Bs, max_gt, R = int(gt_boxes.shape[0]), int(gt_boxes.shape[1]), int(rois.shape[0])
+    with torch.cuda.device(dev):
+        nbytes = int(_lib.lib().wssdl_roi_targets_workspace_bytes(Bs, R, max_gt))
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        counts = torch.zeros((max(Bs, 1), 4), dtype=torch.int32, device=dev)
+        rc = _lib.lib().wssdl_roi_match(_ptr(rois), R, _ptr(gt_boxes), _ptr(num_gt), max(max_gt, 1), Bs,
+                                        int(bool(add_gt)), float(fg_thresh), float(bg_thresh_hi),
+                                        float(bg_thresh_lo), _ptr(ws), nbytes, _ptr(counts), _stream(dev))
+    _lib.check(rc, "wssdl_roi_match")
+    return RoiMatch(rois, gt_boxes, ws, counts[:Bs], Bs)
+
+
+def roi_targets(match, num_classes, inside_weights=(1.0, 1.0, 1.0, 1.0), normalize_means=None,
+                normalize_stds=None, sel=None, sel_off=None, row_off=None, n_rows=None,
+                fg_rois_per_image=0, rois_per_image=0, seed=None):
+    """Second half of _sample_rois + _compute_targets + _get_bbox_regression_labels on the device.
+    Selection: sel / sel_off / row_off (+ n_rows, host-drawn ranks: the parity mode) or seed with
+    fg_rois_per_image / rois_per_image (Philox on the device).  Returns device tensors (rois [N,5],
+    labels [N,1], targets, inside, outside [N,4K], out_counts [Bs,2] i32 or None)."""
+    dev = match.gt_boxes.device
+    Bs, K = match.n_supervised, int(num_classes)
+    if (sel is None) == (seed is None):
+        raise ValueError("pass either host-drawn ranks (sel, sel_off, row_off) or a Philox seed")
+    iw = np.ascontiguousarray(inside_weights, dtype=np.float32)
+    means = stds = None
+    if normalize_means is not None:
+        means = np.ascontiguousarray(normalize_means, dtype=np.float64)
+        stds = np.ascontiguousarray(normalize_stds, dtype=np.float64)
+    with torch.cuda.device(dev):
+        oc = None
+        if sel is not None:
+            mode = _lib.SAMPLE_RANKS
+            packed = np.concatenate([np.asarray(sel_off, np.int32), np.asarray(row_off, np.int32),
+                                     np.asarray(sel, np.int32)])
+            if len(sel_off) != 2 * Bs + 1 or len(row_off) != Bs + 1:
+                raise ValueError("sel_off holds 2*Bs+1 offsets, row_off Bs+1")
+            packed_d = _cuda(packed, torch.int32, dev)          # one H2D for all three
+            sel_off_d, row_off_d = packed_d[:2 * Bs + 1], packed_d[2 * Bs + 1:3 * Bs + 2]
+            sel_d = packed_d[3 * Bs + 2:]
+            N = int(row_off[-1]) if n_rows is None else int(n_rows)
+        else:
+            mode = _lib.SAMPLE_PHILOX
+            sel_d = sel_off_d = row_off_d = None
+            N = Bs * int(rois_per_image)
+            oc = torch.empty((max(Bs, 1), 2), dtype=torch.int32, device=dev)
+        out_rois = torch.empty((N, 5), dtype=torch.float32, device=dev)
+        labels = torch.empty((N, 1), dtype=torch.float32, device=dev)
+        targets = torch.empty((N, 4 * K), dtype=torch.float32, device=dev)
+        inside = torch.empty_like(targets)
+        outside = torch.empty_like(targets)
+        if N == 0 or Bs == 0:
+            return out_rois, labels, targets, inside, outside, (oc[:Bs] if oc is not None else None)
+        rc = _lib.lib().wssdl_roi_targets(
+            _ptr(match.rois), int(match.rois.shape[0]), _ptr(match.gt_boxes),
+            max(int(match.gt_boxes.shape[1]), 1), Bs, K, _ptr(match.workspace), _ptr(match.counts), mode,
+            _ptr(sel_d), _ptr(sel_off_d), _ptr(row_off_d),
+            int(fg_rois_per_image), int(rois_per_image), int(seed or 0) & (2 ** 64 - 1),
+            means.ctypes.data_as(_vp) if means is not None else None,
+            stds.ctypes.data_as(_vp) if stds is not None else None, iw.ctypes.data_as(_vp),
+            _ptr(out_rois), _ptr(labels), _ptr(targets), _ptr(inside), _ptr(outside), _ptr(oc),
+            _stream(dev))
+    _lib.check(rc, "wssdl_roi_targets")
+    return out_rois, labels, targets, inside, outside, (oc[:Bs] if oc is not None else None)
+
+
 # ------------------------------------------------------------------ detection post-processing
 def detect_postprocess(rois, scores, bbox_pred, im_meta, roi_counts=None, roi_stride=None,
                        score_thresh=0.05, nms_thresh=0.3, max_per_image=300, cls_agnostic=False,
