@@ -127,7 +127,7 @@ __device__ __forceinline__ bool iou_ge(const float4 bi, float ai, const float4 b
 // are strictly greater than T.  4 passes of 8 bits, MSB first.  All threads must call.
 template <typename KeyFn>
 __device__ unsigned radix_select(KeyFn key_at, int n, int K, unsigned* s_hist /*256*/,
-                                 unsigned* s_bcast /*4*/, int* n_greater) {
+                                 unsigned* s_bcast /*4*/, int* n_greater, int* n_equal = nullptr) {
   unsigned prefix = 0, prefix_mask = 0;
   int remaining = K;     // rank still to be found inside the current prefix bucket
   int greater = 0;
@@ -159,6 +159,7 @@ __device__ unsigned radix_select(KeyFn key_at, int n, int K, unsigned* s_hist /*
           if (before < (unsigned)remaining && (unsigned)remaining <= before + c[q]) {
             s_bcast[0] = 255 - (8 * lane + q);   // digit of the K-th key
             s_bcast[1] = before;                 // accepted keys above that digit
+            s_bcast[2] = c[q];                   // accepted keys with that digit
           }
           before += c[q];
         }
@@ -166,6 +167,7 @@ __device__ unsigned radix_select(KeyFn key_at, int n, int K, unsigned* s_hist /*
     }
     __syncthreads();
     const unsigned digit = s_bcast[0];
+    if (n_equal) *n_equal = (int)s_bcast[2];      // after the last pass: keys equal to the result
     greater += (int)s_bcast[1];
     remaining -= (int)s_bcast[1];
     prefix |= digit << shift;
@@ -233,13 +235,27 @@ proposals_kernel(const PropParams p) {
   // fail the filter visits the same sequence as filtering first and sorting the rest, so only a
   // few hundred of the 17100 boxes are ever decoded (the full decode was 24 % of the kernel).
   if (tid == 0) s_cnt[1] = 0;
-  for (int a = tid; a < p.NA; a += PT) {
-    const int cell = a / p.A;
-    const int an = a - cell * p.A;
-    const float sc = __ldg(p.cls_prob + ((size_t)img * p.H * p.W + cell) * (2 * p.A) + p.A + an);
-    s_keys[a] = orderable_key(sc);
+  // (eight independent loads in flight per thread: one at a time the 17 strided loads of a thread
+  // were 12 % of the kernel, all of it load latency)
+  {
+    const float* sc_img = p.cls_prob + (size_t)img * p.H * p.W * (2 * p.A) + p.A;
+    for (int a0 = 0; a0 < p.NA; a0 += 8 * PT) {
+      float sc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int a = a0 + q * PT + tid;
+        const int cell = a / p.A;
+        sc[q] = a < p.NA ? __ldg(sc_img + (size_t)a + (size_t)cell * p.A) : 0.f;   // cell*2A + A + an
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int a = a0 + q * PT + tid;
+        if (a < p.NA) s_keys[a] = orderable_key(sc[q]);
+      }
+    }
     if (p.decoded && writer)                  // the intermediate of :116-119, only when asked for
-      reinterpret_cast<float4*>(p.decoded)[(size_t)img * p.NA + a] = decode_anchor(p, img, a, im_h, im_w);
+      for (int a = tid; a < p.NA; a += PT)
+        reinterpret_cast<float4*>(p.decoded)[(size_t)img * p.NA + a] = decode_anchor(p, img, a, im_h, im_w);
   }
   __syncthreads();
 
@@ -256,12 +272,14 @@ proposals_kernel(const PropParams p) {
     // a + 1 >= T2): key and, among ties at T, the highest indices first
     unsigned T = 0, T2 = 0;
     if (want < p.NA) {
-      int n_gt = 0;
-      T = radix_select([&](int i) { return s_keys[i]; }, p.NA, want, s_hist, s_bcast, &n_gt);
+      int n_gt = 0, n_eq = 0;
+      T = radix_select([&](int i) { return s_keys[i]; }, p.NA, want, s_hist, s_bcast, &n_gt, &n_eq);
       const int need_eq = want - n_gt;        // how many keys == T are in (highest indices)
-      int dummy = 0;
-      T2 = radix_select([&](int i) { return s_keys[i] == T ? (unsigned)(i + 1) : 0u; }, p.NA,
-                        need_eq, s_hist, s_bcast, &dummy);
+      if (need_eq < n_eq) {                   // (all ties in: T2 = 0 admits them, no second select)
+        int dummy = 0;
+        T2 = radix_select([&](int i) { return s_keys[i] == T ? (unsigned)(i + 1) : 0u; }, p.NA,
+                          need_eq, s_hist, s_bcast, &dummy);
+      }
     }
     // compact this batch + bitonic sort (ascending in (~key, ~index))
     if (tid == 0) s_cnt[1] = 0;
@@ -277,8 +295,11 @@ proposals_kernel(const PropParams p) {
       }
     }
     __syncthreads();
+    // (element i lives in lane i & 31 of its warp for every i = e * PT + tid: the stages with
+    // j < 32 exchange through shuffles, one barrier per run of them instead of one per stage)
     for (int k = 2; k <= M; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
+      int j = k >> 1;
+      for (; j >= 32; j >>= 1) {
         for (int t = tid; t < M / 2; t += PT) {
           const int i = 2 * t - (t & (j - 1));
           const bool up = ((i & k) == 0);
@@ -287,6 +308,17 @@ proposals_kernel(const PropParams p) {
         }
         __syncthreads();
       }
+      for (int i = tid; i - lane < M; i += PT) {             // whole warps (M may be below 32)
+        unsigned long long x = i < M ? s_sort[i] : ~0ull;
+        const bool up = ((i & k) == 0);
+        for (int jj = j; jj > 0; jj >>= 1) {
+          const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, jj);
+          const bool lower = (i & jj) == 0;                  // I hold the lower index of the pair
+          if ((lower == up) ? (x > y) : (x < y)) x = y;      // keep min at the lower index when up
+        }
+        if (i < M) s_sort[i] = x;
+      }
+      __syncthreads();
     }
     Tp = T;
     T2p = T2;
@@ -388,26 +420,45 @@ proposals_kernel(const PropParams p) {
       }
       __syncthreads();
     }
-    // B: column masks inside the chunk: word g of candidate j = alive i in [64g,64g+63], i<j,
-    //    that suppress j
+    // B: column masks inside the chunk: bit i of candidate j's 256-bit column = alive i < j
+    //    suppresses j.  The four threads of a candidate take the earlier candidates i == g (mod 4):
+    //    every lane of a warp then runs about the same number of tests (j / 4 of them; with one
+    //    64-candidate block per thread most lanes idled while a few ran 64 tests), and the four
+    //    partial columns are OR-ed with two shuffles per word.
     {
       const int j = tid >> 2, g = tid & 3;
-      unsigned long long word = 0;
+      unsigned res[CHUNK / 32];
+#pragma unroll
+      for (int wd = 0; wd < CHUNK / 32; ++wd) res[wd] = 0u;
       const bool alive_j = (s_alive[j >> 5] >> (j & 31)) & 1u;
-      if (alive_j && 64 * g < j) {
-        unsigned long long aw = ((unsigned long long)s_alive[2 * g + 1] << 32) | s_alive[2 * g];
-        const int hi = j - 64 * g;   // bits below hi are earlier candidates
-        if (hi < 64) aw &= (1ull << hi) - 1ull;
+      if (alive_j) {
         const float4 bj = s_cbox[j];
         const float aj = s_carea[j];
-        while (aw) {
-          const int bit = __ffsll((long long)aw) - 1;
-          aw &= aw - 1;
-          const int i = 64 * g + bit;
-          if (iou_ge(s_cbox[i], s_carea[i], bj, aj, p.thr_ge)) word |= 1ull << bit;
+        const unsigned mine = 0x11111111u << g;
+#pragma unroll
+        for (int wd = 0; wd < CHUNK / 32; ++wd) {
+          if (32 * wd < j) {
+            unsigned aw = s_alive[wd] & mine;
+            if (j - 32 * wd < 32) aw &= (1u << (j - 32 * wd)) - 1u;   // earlier candidates only
+            while (aw) {
+              const int bit = __ffs((int)aw) - 1;
+              aw &= aw - 1;
+              const int i = 32 * wd + bit;
+              if (iou_ge(s_cbox[i], s_carea[i], bj, aj, p.thr_ge)) res[wd] |= 1u << bit;
+            }
+          }
         }
       }
-      s_col[j * 4 + g] = word;
+#pragma unroll
+      for (int wd = 0; wd < CHUNK / 32; ++wd) {
+        res[wd] |= __shfl_xor_sync(0xffffffffu, res[wd], 1);
+        res[wd] |= __shfl_xor_sync(0xffffffffu, res[wd], 2);
+      }
+      unsigned lo = 0, hi = 0;
+#pragma unroll
+      for (int wd = 0; wd < CHUNK / 32; wd += 2)
+        if ((wd >> 1) == g) { lo = res[wd]; hi = res[wd + 1]; }
+      s_col[j * 4 + g] = ((unsigned long long)hi << 32) | lo;
     }
     __syncthreads();
     // C: warp 0 resolves the chunk, 32 candidates at a time
