@@ -309,6 +309,36 @@ int wssdl_anchor_targets(const float* labels_pre, const int* argmax_gt, const fl
                          double positive_weight, float* labels_out, float* targets, float* inside,
                          float* outside, int* final_counts, wssdl_stream_t stream);
 
+/* ---------------------------------------------------------------- the hot path as one call
+ * proposal_layer -> roi_pool for a batch of images, the composition the reference runs per
+ * image inside one sess.run (networks/VGGnet_test_bus.py:57-62; rpn_msr/proposal_layer_tf_bus.py
+ * :19-148 feeding roi_pooling_op.cc:89-224).  Same arguments and results as wssdl_proposals
+ * followed by wssdl_roi_pool_fwd on its RoI blob (feat is the [B,H,W,C] map the RPN head ran on),
+ * with two differences: the blob's unused rows (row >= counts[b] of image b's post_nms_topN rows)
+ * carry batch index -1 and pool to zeros / argmax -1, and the pooling skips its RoI grouping
+ * pre-pass because the blob is image-major by construction.  post_nms_topN must be > 0.
+ * rois_ready_event: NULL, or a cudaEvent_t recorded on `stream` between the two stages, when
+ * rois / scores / counts are final: a consumer on another stream (the all-gather of the
+ * detections) can start while the pooling runs.
+ * top [B*post_nms_topN,PH,PW,C], argmax the same shape or NULL. */
+size_t wssdl_hot_path_fwd_workspace_bytes(int B, int post_nms_topN, int PH, int PW);
+
+int wssdl_hot_path_fwd(const float* feat, const float* cls_prob, const float* bbox_pred,
+                       const float* im_info, int info_stride, int B, int H, int W, int C, int A,
+                       const float* base_anchors, int feat_stride, int pre_nms_topN,
+                       int post_nms_topN, double nms_thresh, int nms_mode, float min_size, int PH,
+                       int PW, float spatial_scale, int bin_mode, float* rois, float* scores,
+                       int* counts, float* top, int* argmax, void* workspace,
+                       size_t workspace_bytes, wssdl_stream_t stream, void* rois_ready_event);
+
+/* wssdl_roi_pool_fwd for image-major RoIs: row r belongs to image r / roi_stride (R = B *
+ * roi_stride); rows whose batch index is not their block's image pool to zeros / -1.  The layout
+ * wssdl_proposals writes; saves the RoI grouping pre-pass of the sorted-bins kernel. */
+int wssdl_roi_pool_fwd_grouped(const float* bottom, const float* rois, int roi_stride, int B,
+                               int H, int W, int C, int PH, int PW, float spatial_scale,
+                               int bin_mode, float* top, int* argmax, void* workspace,
+                               size_t workspace_bytes, wssdl_stream_t stream);
+
 /* ---------------------------------------------------------------- proposal targets, on device
  * Replaces proposal_target_layer / proposal_target_layer_joint for the supervised images
  * (rpn_msr/proposal_target_layer_tf_bus.py:15-184) and _sample_rois (:228-280),

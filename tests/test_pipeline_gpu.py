@@ -93,3 +93,37 @@ def test_c4_full_batch_properties_and_kernel_agreement(oracle_mod, tuning):
         top2, arg2 = ops.roi_pool_forward(x, r, 7, 7, 1 / 16.)
         assert torch.equal(top2, top) and torch.equal(arg2, arg), kern
         del top2, arg2
+
+
+@pytest.mark.parametrize("B,kern", [(1, None), (3, None), (5, "sorted"), (20, None), (3, "direct")])
+def test_fused_entry_equals_the_two_ops_back_to_back(B, kern, tuning):
+    """wssdl_hot_path_fwd (one call) against wssdl_proposals + wssdl_roi_pool_fwd: same RoIs,
+    scores, counts and pooled rows for every kept RoI; the unused rows of an image's block carry
+    batch index -1 and pool to zeros / argmax -1 whichever forward kernel runs.  pre_nms_topN = 200
+    < post_nms_topN = 300 leaves at least 100 unused rows per image."""
+    if kern:
+        tuning("roi_fwd_kernel", kern)
+    feat, cls, reg, info = _inputs(720 + B, B)
+    x = torch.from_numpy(feat).cuda()
+    hot = HotPath(pre_nms_topN=200)
+    ready = torch.cuda.Event()
+    ready.record()
+    f = hot.run(x, cls, reg, info, rois_ready=ready)
+    u = hot.run(x, cls, reg, info, fused=False)
+    ready.synchronize()
+    cnt = f["counts"].cpu().numpy()
+    assert np.array_equal(cnt, u["counts"].cpu().numpy()) and cnt.max() <= 200 and cnt.min() > 0
+    assert torch.equal(f["scores"], u["scores"])
+    valid = (torch.arange(300, device="cuda")[None, :] < f["counts"][:, None]).reshape(-1)
+    assert torch.equal(f["rois"][valid], u["rois"][valid])
+    assert torch.equal(f["top"][valid], u["top"][valid])
+    assert torch.equal(f["argmax"][valid], u["argmax"][valid])
+    pad = ~valid
+    assert bool(torch.all(f["rois"][pad][:, 0] == -1)) and not bool(f["rois"][pad][:, 1:].any())
+    assert not bool(f["top"][pad].any()) and bool(torch.all(f["argmax"][pad] == -1))
+    # the grouped RoI-pool entry on the fused call's blob: the same bytes
+    top, arg = ops.roi_pool_forward_grouped(x, f["rois"], 300, 7, 7, 1 / 16.)
+    assert torch.equal(top, f["top"]) and torch.equal(arg, f["argmax"])
+    # without argmax
+    g = hot.run(x, cls, reg, info, need_argmax=False)
+    assert g["argmax"] is None and torch.equal(g["top"], f["top"])

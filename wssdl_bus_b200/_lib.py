@@ -52,6 +52,11 @@ SIGNATURES = {
     "wssdl_anchor_label_counts": (_i, [_vp, _i, _i, _vp, _vp]),
     "wssdl_anchor_targets": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp,
                                   ctypes.c_ulonglong, _vp, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wssdl_hot_path_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "wssdl_hot_path_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _d, _i, _f,
+                                _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "wssdl_roi_pool_fwd_grouped": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp,
+                                        _sz, _vp]),
     "wssdl_roi_targets_workspace_bytes": (_sz, [_i, _i, _i]),
     "wssdl_roi_match": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d, _vp, _sz, _vp, _vp]),
     "wssdl_roi_targets": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i,

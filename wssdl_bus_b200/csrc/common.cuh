@@ -24,6 +24,19 @@
 // Process-wide tuning switch (capi.cu; include/wssdl_b200.h: wssdl_set_tuning).
 int wssdl_tuning(int key);
 
+// Internal forms of two public entries, used by the fused hot-path entry (hot_path.cu):
+// the RoI-pool forward with image-major RoIs (roi_pool.cu) and the proposals launch with a chosen
+// batch index for the padding rows behind an image's RoIs (proposal.cu).
+int wssdl_roi_pool_fwd_impl(const float* bottom, const float* rois, int B, int H, int W, int C,
+                            int R, int PH, int PW, float spatial_scale, int bin_mode, float* top,
+                            int* argmax, void* workspace, size_t workspace_bytes,
+                            wssdl_stream_t stream, int grouped_stride);
+int wssdl_proposals_impl(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                         int info_stride, int B, int H, int W, int A, const float* base_anchors,
+                         int feat_stride, int pre_nms_topN, int post_nms_topN, double nms_thresh,
+                         int nms_mode, float min_size, float* rois, float* scores, int* anchor_idx,
+                         int* counts, float* decoded, wssdl_stream_t stream, float pad_batch_index);
+
 static inline cudaStream_t to_cuda(wssdl_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

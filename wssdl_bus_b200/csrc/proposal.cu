@@ -55,6 +55,7 @@ struct PropParams {
   int kpad;                      // M: candidates sorted at a time (power of two)
   float thr_ge;                  // smallest float whose double value is >= nms_thresh
   float min_size;
+  float pad_batch;               // batch index written into the unused rows of an image's block
   float* rois;
   float* scores;
   int* anchor_idx;
@@ -534,7 +535,8 @@ proposals_kernel(const PropParams p) {
   if constexpr (CS > 1) cg::this_cluster().sync();   // no peer may still write into my slots
   if (!writer) return;
   // zero-fill the unused tail so the blob is deterministic
-  for (int i = nkept * 5 + tid; i < post * 5; i += PT) p.rois[(size_t)img * post * 5 + i] = 0.f;
+  for (int i = nkept * 5 + tid; i < post * 5; i += PT)
+    p.rois[(size_t)img * post * 5 + i] = (i % 5 == 0) ? p.pad_batch : 0.f;
   for (int i = nkept + tid; i < post; i += PT) {
     if (p.scores) p.scores[(size_t)img * post + i] = 0.f;
     if (p.anchor_idx) p.anchor_idx[(size_t)img * post + i] = -1;
@@ -574,6 +576,16 @@ extern "C" int wssdl_proposals(const float* cls_prob, const float* bbox_pred,
                                float* scores, int* anchor_idx, int* counts, float* decoded,
                                void* workspace, size_t workspace_bytes, wssdl_stream_t stream) {
   (void)workspace; (void)workspace_bytes;
+  return wssdl_proposals_impl(cls_prob, bbox_pred, im_info, info_stride, B, H, W, A, base_anchors,
+                              feat_stride, pre_nms_topN, post_nms_topN, nms_thresh, nms_mode,
+                              min_size, rois, scores, anchor_idx, counts, decoded, stream, 0.f);
+}
+
+int wssdl_proposals_impl(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                         int info_stride, int B, int H, int W, int A, const float* base_anchors,
+                         int feat_stride, int pre_nms_topN, int post_nms_topN, double nms_thresh,
+                         int nms_mode, float min_size, float* rois, float* scores, int* anchor_idx,
+                         int* counts, float* decoded, wssdl_stream_t stream, float pad_batch_index) {
   if (B < 0 || H <= 0 || W <= 0 || A <= 0 || info_stride < 3) return WSSDL_EINVAL;
   if (nms_mode != WSSDL_NMS_GE_F64 && nms_mode != WSSDL_NMS_GT_F32) return WSSDL_EINVAL;
   if (B == 0) return WSSDL_OK;
@@ -625,6 +637,7 @@ extern "C" int wssdl_proposals(const float* cls_prob, const float* bbox_pred,
   else if ((double)f < nms_thresh) f = nextafterf(f, INFINITY);
   p.thr_ge = f;
   p.min_size = min_size;
+  p.pad_batch = pad_batch_index;
   p.rois = rois; p.scores = scores; p.anchor_idx = anchor_idx; p.counts = counts;
   p.decoded = decoded;
   // base anchors: HOST pointer (generate_anchors runs on the host, as in the reference)

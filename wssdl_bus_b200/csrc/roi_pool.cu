@@ -1176,6 +1176,28 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
                                   int C, int R, int PH, int PW, float spatial_scale,
                                   int bin_mode, float* top, int* argmax, void* workspace,
                                   size_t workspace_bytes, wssdl_stream_t stream) {
+  return wssdl_roi_pool_fwd_impl(bottom, rois, B, H, W, C, R, PH, PW, spatial_scale, bin_mode, top,
+                                 argmax, workspace, workspace_bytes, stream, 0);
+}
+
+extern "C" int wssdl_roi_pool_fwd_grouped(const float* bottom, const float* rois, int roi_stride,
+                                          int B, int H, int W, int C, int PH, int PW,
+                                          float spatial_scale, int bin_mode, float* top,
+                                          int* argmax, void* workspace, size_t workspace_bytes,
+                                          wssdl_stream_t stream) {
+  if (roi_stride < 0 || B < 0 || (long long)roi_stride * B >= (1ll << 31)) return WSSDL_EINVAL;
+  return wssdl_roi_pool_fwd_impl(bottom, rois, B, H, W, C, roi_stride * B, PH, PW, spatial_scale,
+                                 bin_mode, top, argmax, workspace, workspace_bytes, stream,
+                                 roi_stride);
+}
+
+// grouped_stride > 0: the caller guarantees image-major RoIs (row r belongs to image
+// r / grouped_stride; rows with another batch index -- the -1 padding rows of the hot-path
+// entry -- pool to zeros / -1 in every kernel): the sorted-bins pre-pass then needs no RoI lists.
+int wssdl_roi_pool_fwd_impl(const float* bottom, const float* rois, int B, int H, int W, int C,
+                            int R, int PH, int PW, float spatial_scale, int bin_mode, float* top,
+                            int* argmax, void* workspace, size_t workspace_bytes,
+                            wssdl_stream_t stream, int grouped_stride) {
   // attribute checks of the op (roi_pooling_op.cc:73-82) plus pointer sanity
   if (B < 0 || H < 0 || W < 0 || C < 0 || R < 0 || PH < 0 || PW < 0) return WSSDL_EINVAL;
   if (bin_mode != WSSDL_BIN_CPU_TRUNC && bin_mode != WSSDL_BIN_GPU_CEIL) return WSSDL_EINVAL;
@@ -1197,7 +1219,8 @@ extern "C" int wssdl_roi_pool_fwd(const float* bottom, const float* rois, int B,
   const BandPlan& bp = choice.bp;
   if (choice.kernel == FWD_BINS) {
     WSSDL_RETURN_IF_CUDA(launch_fwd_bins(choice.np, bottom, rois, B, H, W, C, R, PH, PW,
-                                         spatial_scale, bin_mode, top, argmax, workspace, s));
+                                         spatial_scale, bin_mode, top, argmax, workspace, s,
+                                         grouped_stride));
     return WSSDL_OK;
   }
   if (choice.kernel == FWD_BAND) {

@@ -295,6 +295,7 @@ struct SortArgs {
   float spatial_scale;
   int bin_mode;
   int rch;              // RoIs whose geometry is resident at a time
+  int stride;           // > 0: image-major RoIs, image b owns rows [b*stride, (b+1)*stride)
   BandGeom bg;
   FastDiv divPH, divStep;
 };
@@ -319,7 +320,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
   // ---- this image's RoIs, and how many RoIs the images before it hold
   const int* list = nullptr;
   int n_img, before;
-  if (a.perm != nullptr) {
+  if (a.stride > 0) {                               // grouped: no lists at all
+    before = img * a.stride;
+    n_img = valid_img ? a.stride : 0;
+  } else if (a.perm != nullptr) {
     before = a.img_start[img];
     n_img = a.img_start[img + 1] - before;
     list = a.perm + before;
@@ -348,16 +352,19 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
   // RoI's PW bins (9 fields of 7 bits: 0, 1..7, >= 8 cells) is shared by its PH rows
   auto geometry = [&](int c0, int nb) {
     for (int rl = tid; rl < nb; rl += S_THREADS) {
-      const int n = list ? list[c0 + rl] : (int)s_list[c0 + rl];
+      const int n = a.stride > 0 ? before + c0 + rl : (list ? list[c0 + rl] : (int)s_list[c0 + rl]);
       s_nb[rl] = n * PH * PW;
       const RoiCells g = roi_cells(a.rois + (size_t)n * 5, a.spatial_scale, PH, PW);
-      s_sh[rl] = g.start_h;
-      s_bh[rl] = g.bin_h;
+      // grouped: a row whose batch index is not its block's image (the padding rows behind an
+      // image's RoIs carry -1) has empty bins only
+      const bool mine = a.stride <= 0 || roi_bucket(__ldg(a.rois + (size_t)n * 5), a.B) == img;
+      s_sh[rl] = mine ? g.start_h : 0;
+      s_bh[rl] = mine ? g.bin_h : 0.f;
       unsigned long long wf = 0;
       for (int pw = 0; pw < PW; ++pw) {
         int ws = min(max(edge_lo(mode, pw, g.bin_w) + g.start_w, 0), W);
         int we = min(max(edge_hi(mode, pw, g.bin_w) + g.start_w, 0), W);
-        if (!valid_img) ws = we = 0;
+        if (!valid_img || !mine) ws = we = 0;
         const int nw = max(we - ws, 0);
         s_we[rl * PW + pw] = (unsigned short)(ws | (min(nw, 255) << 8));
         wf += 1ull << (7 * min(nw, N_DIM));
@@ -866,10 +873,11 @@ BinsPlan wssdl_roi::plan_bins(int B, int H, int W, int C, int R, int PH, int PW,
 cudaError_t wssdl_roi::launch_fwd_bins(const BinsPlan& p, const float* bottom, const float* rois,
                                        int B, int H, int W, int C, int R, int PH, int PW,
                                        float spatial_scale, int bin_mode, float* top, int* argmax,
-                                       void* workspace, cudaStream_t s) {
+                                       void* workspace, cudaStream_t s, int grouped_stride) {
   int* img_start = nullptr;
   int* perm = nullptr;
-  if (!p.scan) {
+  if (grouped_stride > 0 && (long long)grouped_stride * B != R) return cudaErrorInvalidValue;
+  if (!p.scan && grouped_stride <= 0) {
     cudaError_t e = launch_roi_bucket(rois, R, B, workspace, s, &img_start, &perm);
     if (e != cudaSuccess) return e;
   }
@@ -884,6 +892,7 @@ cudaError_t wssdl_roi::launch_fwd_bins(const BinsPlan& p, const float* bottom, c
   sa.spatial_scale = spatial_scale;
   sa.bin_mode = bin_mode;
   sa.rch = p.sort_rch;
+  sa.stride = grouped_stride > 0 ? grouped_stride : 0;
   sa.bg = p.g;
   sa.divPH = make_fastdiv((unsigned)PH);
   sa.divStep = make_fastdiv((unsigned)p.g.step);

@@ -154,6 +154,6 @@ BinsPlan plan_bins(int B, int H, int W, int C, int R, int PH, int PW, bool align
 cudaError_t launch_fwd_bins(const BinsPlan& p, const float* bottom, const float* rois, int B,
                             int H, int W, int C, int R, int PH, int PW, float spatial_scale,
                             int bin_mode, float* top, int* argmax, void* workspace,
-                            cudaStream_t s);
+                            cudaStream_t s, int grouped_stride = 0);
 
 }  // namespace wssdl_roi

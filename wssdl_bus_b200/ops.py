@@ -97,6 +97,33 @@ def roi_pool_forward(bottom, rois, pooled_height, pooled_width, spatial_scale, b
     return top, argmax
 
 
+def roi_pool_forward_grouped(bottom, rois, roi_stride, pooled_height, pooled_width, spatial_scale,
+                             bin_mode="cpu", need_argmax=True):
+    """roi_pool_forward for image-major RoIs (wssdl_roi_pool_fwd_grouped): row r of rois
+    [B*roi_stride,5] belongs to image r // roi_stride -- the blob proposals() writes; rows whose
+    batch index says otherwise pool to zeros / -1.  Skips the RoI grouping pre-pass."""
+    bottom = _cuda(bottom, torch.float32)
+    rois = _cuda(rois, torch.float32, bottom.device)
+    if bottom.dim() != 4 or rois.dim() != 2 or rois.shape[1] != 5:
+        raise ValueError("bottom [B,H,W,C], rois [B*roi_stride,5]")
+    B, H, W, C = bottom.shape
+    if rois.shape[0] != B * int(roi_stride):
+        raise ValueError("rois must hold roi_stride rows per image")
+    R = rois.shape[0]
+    with torch.cuda.device(bottom.device):
+        top = torch.empty((R, pooled_height, pooled_width, C), dtype=torch.float32,
+                          device=bottom.device)
+        argmax = torch.empty_like(top, dtype=torch.int32) if need_argmax else None
+        ws = _workspace(_lib.lib().wssdl_roi_pool_fwd_workspace_bytes(B, R, pooled_height, pooled_width),
+                        bottom.device)
+        rc = _lib.lib().wssdl_roi_pool_fwd_grouped(
+            _ptr(bottom), _ptr(rois), int(roi_stride), B, H, W, C, pooled_height, pooled_width,
+            float(spatial_scale), _bin_mode(bin_mode), _ptr(top), _ptr(argmax), _vp(ws.data_ptr()),
+            ws.numel(), _stream(bottom.device))
+    _lib.check(rc, "wssdl_roi_pool_fwd_grouped")
+    return top, argmax
+
+
 def roi_pool_backward(bottom_shape, rois, argmax, grad, pooled_height, pooled_width,
                       spatial_scale, deterministic=False):
     """RoiPoolGrad.  Returns bottom_diff [B,H,W,C] f32."""
@@ -381,6 +408,62 @@ def proposals(cls_prob, bbox_pred, im_info, base_anchors, feat_stride, pre_nms_t
     if want_decoded:
         out["decoded"] = decoded
     return out
+
+
+def hot_path_forward(feat, cls_prob, bbox_pred, im_info, base_anchors, feat_stride, pre_nms_topN,
+                     post_nms_topN, nms_thresh, min_size, pooled_height, pooled_width,
+                     spatial_scale, bin_mode="cpu", need_argmax=True, out=None, nms_mode=NMS_GE_F64,
+                     rois_ready=None):
+    """proposal_layer -> roi_pool as ONE call (wssdl_hot_path_fwd; VGGnet_test_bus.py:57-62).
+    feat [B,H,W,C], cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A], im_info [B,>=3].  Returns the dict
+    of proposals() (without anchor_idx) + top / argmax [B*post,PH,PW,C].  Unused rows of an image's
+    post_nms_topN RoI slots carry batch index -1 and pool to zeros / -1.
+    rois_ready: a torch.cuda.Event (recorded at least once before) that the call records between
+    its two stages, when rois / scores / counts are final."""
+    feat = _cuda(feat, torch.float32)
+    dev = feat.device
+    cls_prob = _cuda(cls_prob, torch.float32, dev)
+    bbox_pred = _cuda(bbox_pred, torch.float32, dev)
+    im_info = _cuda(im_info, torch.float32, dev)
+    if im_info.dim() == 1:
+        im_info = im_info.reshape(1, -1)
+    base = np.ascontiguousarray(base_anchors, dtype=np.float32)
+    A = base.shape[0]
+    if feat.dim() != 4 or cls_prob.dim() != 4:
+        raise ValueError("feat [B,H,W,C], cls_prob [B,H,W,2A]")
+    B, H, W, C = feat.shape
+    if (tuple(cls_prob.shape) != (B, H, W, 2 * A) or tuple(bbox_pred.shape) != (B, H, W, 4 * A)
+            or im_info.shape[0] != B):
+        raise ValueError("shape mismatch: feat [B,H,W,C], cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A], "
+                         "im_info [B,3+]")
+    post, PH, PW = int(post_nms_topN), int(pooled_height), int(pooled_width)
+    if post <= 0:
+        raise ValueError("the fused hot path needs post_nms_topN > 0 (the stride of the RoI blob)")
+    with torch.cuda.device(dev):
+        if out is not None:
+            rois, scores, counts = out
+            if (tuple(rois.shape) != (B * post, 5) or tuple(scores.shape) != (B * post,) or
+                    tuple(counts.shape) != (B,) or rois.dtype != torch.float32 or
+                    scores.dtype != torch.float32 or counts.dtype != torch.int32 or
+                    not (rois.is_contiguous() and scores.is_contiguous() and counts.is_contiguous())
+                    or rois.device != dev):
+                raise ValueError("out = (rois [B*post,5] f32, scores [B*post] f32, counts [B] i32), "
+                                 "contiguous, on the inputs' device")
+        else:
+            rois = torch.empty((B * post, 5), dtype=torch.float32, device=dev)
+            scores = torch.empty((B * post,), dtype=torch.float32, device=dev)
+            counts = torch.empty((B,), dtype=torch.int32, device=dev)
+        top = torch.empty((B * post, PH, PW, C), dtype=torch.float32, device=dev)
+        argmax = torch.empty_like(top, dtype=torch.int32) if need_argmax else None
+        ws = _workspace(_lib.lib().wssdl_hot_path_fwd_workspace_bytes(B, post, PH, PW), dev)
+        rc = _lib.lib().wssdl_hot_path_fwd(
+            _ptr(feat), _ptr(cls_prob), _ptr(bbox_pred), _ptr(im_info), im_info.shape[1], B, H, W, C, A,
+            base.ctypes.data_as(_vp), int(feat_stride), int(pre_nms_topN), post, float(nms_thresh),
+            int(nms_mode), float(min_size), PH, PW, float(spatial_scale), _bin_mode(bin_mode),
+            _ptr(rois), _ptr(scores), _ptr(counts), _ptr(top), _ptr(argmax), _vp(ws.data_ptr()),
+            ws.numel(), _stream(dev), _vp(rois_ready.cuda_event) if rois_ready is not None else None)
+    _lib.check(rc, "wssdl_hot_path_fwd")
+    return dict(rois=rois, scores=scores, counts=counts, post_nms_topN=post, top=top, argmax=argmax)
 
 
 def compact_rois(out):

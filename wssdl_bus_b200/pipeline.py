@@ -60,18 +60,31 @@ class HotPath:
         self.feat_stride = feat_stride
         self.base = generate_anchors(scales=np.array(anchor_scales))
         self.bin_mode = bin_mode
-        # kernels launched by one run(): proposals + roi_pool_fwd
-        self.launches_per_run = 2
+        # host calls of one run(): the fused wssdl_hot_path_fwd entry (proposals kernel + bin-sort
+        # pre-pass + pooling kernel on the C4 shapes)
+        self.launches_per_run = 3
 
-    def run(self, feat, cls_prob, bbox_pred, im_info, need_argmax=True, blob=None):
+    def run(self, feat, cls_prob, bbox_pred, im_info, need_argmax=True, blob=None, fused=True,
+            rois_ready=None):
         """Device tensors in, device tensors out, no synchronisation.
         feat [B,H,W,C], cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A], im_info [B,3+].
         blob: a DetectionBlob the proposals are written into (for the all-gather).
-        Rows >= counts[b] of an image's `post` RoI slots are zero RoIs (batch 0, empty box):
-        their pooled rows are defined (the cell (0,0) of image 0) but carry no detection."""
+        fused (default): one wssdl_hot_path_fwd call; rows >= counts[b] of an image's `post` RoI
+        slots carry batch index -1 and their pooled rows are zeros / argmax -1.
+        rois_ready: torch.cuda.Event recorded when rois / scores / counts are final (before the
+        pooling), so that their all-gather can run on another stream meanwhile.
+        fused=False: wssdl_proposals then wssdl_roi_pool_fwd, the two public ops back to back (the
+        unused rows are then zero RoIs of image 0 and pool its cell (0,0))."""
+        outv = None if blob is None else blob.views()
+        if fused and self.post > 0:
+            return ops.hot_path_forward(feat, cls_prob, bbox_pred, im_info, self.base,
+                                        self.feat_stride, self.pre, self.post, self.thresh,
+                                        self.min_size, self.pooled_h, self.pooled_w, self.scale,
+                                        self.bin_mode, need_argmax, out=outv, rois_ready=rois_ready)
         p = ops.proposals(cls_prob, bbox_pred, im_info, self.base, self.feat_stride, self.pre,
-                          self.post, self.thresh, self.min_size,
-                          out=None if blob is None else blob.views())
+                          self.post, self.thresh, self.min_size, out=outv)
+        if rois_ready is not None:
+            rois_ready.record()
         top, argmax = ops.roi_pool_forward(feat, p["rois"], self.pooled_h, self.pooled_w,
                                            self.scale, self.bin_mode, need_argmax)
         p["top"], p["argmax"] = top, argmax
@@ -247,7 +260,7 @@ class HostPipeline:
                 p = self.hot.run(d["feat"][:n], d["cls"][:n], d["reg"][:n], d["info"][:n],
                                  self.need_argmax)
                 # batch indices are chunk-local on the device; make them global for the host
-                # (valid rows only: the slots behind counts[b] stay all-zero rows)
+                # (valid rows only: the slots behind counts[b] keep batch index -1)
                 rois = p["rois"]
                 valid = (self._slot[None, :] < p["counts"][:, None]).reshape(-1)
                 rois[:, 0] += valid.to(rois.dtype) * float(b0)
