@@ -55,11 +55,16 @@ enum {
                                        (WSSDL_ROI_FWD_CHUNKS)                                    */
   WSSDL_TUNE_NMS_SWEEP_CLUSTER = 3, /* -1 by size, 0 single-CTA sweep, 1 cluster sweep
                                        (WSSDL_NMS_SWEEP_CLUSTER)                                 */
-  WSSDL_TUNE_PROPOSALS_CLUSTER = 4, /* -1 by shape, 0 one CTA per image, 1 cluster per image
+  WSSDL_TUNE_PROPOSALS_CLUSTER = 4, /* -1 (or 1) by shape: the largest cluster of 2 / 4 / 8 CTAs
+                                       per image whose B clusters are resident at once, else one
+                                       CTA per image; 0 one CTA per image; 2, 4, 8 that size
                                        (WSSDL_PROPOSALS_CLUSTER)                                 */
   WSSDL_TUNE_ROI_FWD_THREADS = 5,   /* sorted bins: threads per pooling CTA, 0 = default,
                                        1024 (one CTA per SM) or 512 (two)  (WSSDL_ROI_FWD_THREADS) */
-  WSSDL_TUNE_COUNT = 6
+  WSSDL_TUNE_PDL = 6,               /* programmatic dependent launch between the kernels of one
+                                       call (pre-pass -> pooling, proposals -> pre-pass): 1 on
+                                       (default), 0 off */
+  WSSDL_TUNE_COUNT = 7
 };
 int wssdl_set_tuning(int key, int value);
 int wssdl_get_tuning(int key);

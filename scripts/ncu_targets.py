@@ -54,7 +54,7 @@ elif what.startswith("roi4"):
     from wssdl_bus_b200 import _lib
     from wssdl_bus_b200.pipeline import HotPath
     parts = what.split(":")
-    nimg = 256
+    nimg = int(os.environ.get("NCU_IMAGES", "256"))
     cls, reg, info = syn.rpn_outputs(0, nimg, 38, 50, 9)
     hot = HotPath()
     rois = ops.proposals(cls, reg, info, hot.base, 16, hot.pre, hot.post, hot.thresh, hot.min_size)["rois"]
@@ -68,5 +68,8 @@ elif what.startswith("roi4"):
     if len(parts) > 4:
         _lib.set_tuning("roi_fwd_threads", int(parts[4]))
     for _ in range(3):
-        ops.roi_pool_forward(x, rois, 7, 7, 1 / 16.)
+        if os.environ.get("NCU_GROUPED"):
+            ops.roi_pool_forward_grouped(x, rois, 300, 7, 7, 1 / 16.)
+        else:
+            ops.roi_pool_forward(x, rois, 7, 7, 1 / 16.)
 torch.cuda.synchronize()

@@ -33,7 +33,7 @@ g = torch.randn_like(top)
 for det in (False, True):
     ops.roi_pool_backward((B, H, W, C), rois, arg, g, 7, 7, 1 / 16., deterministic=det)
 cls, reg, info = syn.rpn_outputs(3, B, H, W, 9)
-for cl in (0, 1):     # one CTA per image / cluster of 8 CTAs per image
+for cl in (0, 2, 4, 8):     # one CTA per image / cluster of 2, 4, 8 CTAs per image
     _lib.set_tuning("proposals_cluster", cl)
     ops.proposals(cls, reg, info, generate_anchors(), 16, 6000, 300, 0.7, 16)
     ops.proposals(cls, reg, info, generate_anchors(), 16, 2000, 500, 0.7, 16, want_decoded=True)

@@ -15,12 +15,13 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
-@pytest.fixture(autouse=True, params=["cta", "cluster"])
+@pytest.fixture(autouse=True, params=["cta", "cluster2", "cluster4", "cluster8"])
 def proposals_variant(request, tuning):
-    """Every test runs twice: one CTA per image, and a thread-block cluster of 8 CTAs per
-    image (csrc/proposal.cu: the keep-list NMS is split over the cluster and its partial
-    bitmaps are exchanged through distributed shared memory).  The default picks by batch size."""
-    tuning("proposals_cluster", 1 if request.param == "cluster" else 0)
+    """Every test runs four times: one CTA per image, and thread-block clusters of 2 / 4 / 8 CTAs
+    per image (csrc/proposal.cu: both stages of the keep-list NMS rounds are split over the
+    cluster, alive bits and column masks are exchanged through distributed shared memory).  The
+    default picks by batch size."""
+    tuning("proposals_cluster", 0 if request.param == "cta" else int(request.param[7:]))
     return request.param
 
 

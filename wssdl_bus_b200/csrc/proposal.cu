@@ -36,6 +36,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -194,8 +196,7 @@ template <int CS>
 __global__ void __launch_bounds__(PT, 1)
 proposals_kernel(const PropParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ unsigned s_xchg[2][CS][XCHG_WORDS];    // [slot set][source CTA][word]
-  __shared__ unsigned s_sup[XCHG_WORDS];            // this CTA's partial "suppressed" bitmap
+  __shared__ unsigned s_sup[XCHG_WORDS];            // cluster rounds: alive words of my candidates
   __shared__ int s_wcnt[PT / 32];                   // per-warp counts of a block-wide compaction
   namespace cg = cooperative_groups;
   int crank = 0;
@@ -207,6 +208,11 @@ proposals_kernel(const PropParams p) {
     cg::this_cluster().sync();
   }
   const bool writer = crank == 0;
+  if (threadIdx.x < XCHG_WORDS) s_sup[threadIdx.x] = 0u;
+  // programmatic dependent launch: a kernel queued behind this one with the attribute (the
+  // RoI-pool pre-pass of the fused hot-path entry) may become resident now; it waits for this
+  // grid's completion (griddepcontrol.wait) before it reads the RoIs
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // layout: sort buffer (kpad u64) | histogram/scalars | keys (NA u32, rounded to 4) | per-chunk
   // NMS state | kept list
   unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -215,12 +221,12 @@ proposals_kernel(const PropParams p) {
   int* s_cnt = reinterpret_cast<int*>(s_bcast + 4);                            // [4]
   unsigned* s_keys = reinterpret_cast<unsigned*>(s_cnt + 4);                   // [NA]
   float4* s_cbox = reinterpret_cast<float4*>(s_keys + ((p.NA + 3) & ~3));      // [CHUNK]
-  unsigned long long* s_col = reinterpret_cast<unsigned long long*>(s_cbox + CHUNK);  // [CHUNK][4]
-  float* s_carea = reinterpret_cast<float*>(s_col + CHUNK * 4);                // [CHUNK]
+  unsigned long long* s_col = reinterpret_cast<unsigned long long*>(s_cbox + CHUNK);  // [2][CHUNK][4]
+  float* s_carea = reinterpret_cast<float*>(s_col + 2 * CHUNK * 4);            // [CHUNK]
   int* s_cidx = reinterpret_cast<int*>(s_carea + CHUNK);                       // [CHUNK]
   unsigned* s_ckey = reinterpret_cast<unsigned*>(s_cidx + CHUNK);              // [CHUNK]
-  unsigned* s_alive = s_ckey + CHUNK;                                          // [CHUNK/32]
-  unsigned* s_kmask = s_alive + CHUNK / 32;                                    // [CHUNK/32]
+  unsigned* s_alive = s_ckey + CHUNK;                                          // [2][CHUNK/32]
+  unsigned* s_kmask = s_alive + 2 * (CHUNK / 32);                              // [CHUNK/32]
   float4* s_kbox = reinterpret_cast<float4*>(s_kmask + CHUNK / 32);            // [post]
   float* s_karea = reinterpret_cast<float*>(s_kbox + p.post_nms_topN);         // [post]
 
@@ -369,6 +375,9 @@ proposals_kernel(const PropParams p) {
       }
     }
     __syncthreads();
+    unsigned long long* const colp = s_col + (CS > 1 ? (round & 1) * CHUNK * 4 : 0);
+    unsigned* const alivep = s_alive + (CS > 1 ? (round & 1) * (CHUNK / 32) : 0);
+    if constexpr (CS == 1) {
     // A: candidate (tid>>2) against kept entries tid&3, +4, +8, ...
     {
       const int cand = tid >> 2;
@@ -376,51 +385,22 @@ proposals_kernel(const PropParams p) {
       if (cand < nc) {
         const float4 bj = s_cbox[cand];
         const float aj = s_carea[cand];
-        for (int k = (tid & 3) + 4 * crank; k < nkept; k += 4 * CS) {
+        for (int k = tid & 3; k < nkept; k += 4) {
           if (iou_ge(s_kbox[k], s_karea[k], bj, aj, p.thr_ge)) { sup = 1; break; }
         }
       }
       sup |= __shfl_xor_sync(0xffffffffu, sup, 1);
       sup |= __shfl_xor_sync(0xffffffffu, sup, 2);
       // lanes 0,4,8,...: 8 candidates per warp -> one byte of the alive bitmap
-      if constexpr (CS == 1) {
-        const unsigned bal = __ballot_sync(0xffffffffu, !sup && cand < nc);
-        if (lane == 0) {
-          unsigned byte = 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, !sup && cand < nc);
+      if (lane == 0) {
+        unsigned byte = 0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) byte |= ((bal >> (4 * q)) & 1u) << q;
-          reinterpret_cast<unsigned char*>(s_alive)[warp] = (unsigned char)byte;
-        }
-      } else {
-        const unsigned bal = __ballot_sync(0xffffffffu, sup && cand < nc);
-        if (lane == 0) {
-          unsigned byte = 0;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) byte |= ((bal >> (4 * q)) & 1u) << q;
-          reinterpret_cast<unsigned char*>(s_sup)[warp] = (unsigned char)byte;
-        }
+        for (int q = 0; q < 8; ++q) byte |= ((bal >> (4 * q)) & 1u) << q;
+        reinterpret_cast<unsigned char*>(s_alive)[warp] = (unsigned char)byte;
       }
     }
     __syncthreads();
-    if constexpr (CS > 1) {
-      cg::cluster_group cluster = cg::this_cluster();
-      const int set = round & 1;
-      if (tid < CS * XCHG_WORDS) {                  // my 256 bits into every CTA's slot [crank]
-        const int peer = tid / XCHG_WORDS, w = tid % XCHG_WORDS;
-        unsigned* remote = cluster.map_shared_rank(&s_xchg[0][0][0], peer);
-        remote[(set * CS + crank) * XCHG_WORDS + w] = s_sup[w];
-      }
-      cluster.sync();
-      if (tid < XCHG_WORDS) {
-        unsigned any = 0;
-#pragma unroll
-        for (int r = 0; r < CS; ++r) any |= s_xchg[set][r][tid];
-        const int lo = 32 * tid;                    // candidates lo .. lo+31 of this round
-        const unsigned valid = nc >= lo + 32 ? 0xffffffffu : (nc > lo ? (1u << (nc - lo)) - 1u : 0u);
-        s_alive[tid] = ~any & valid;
-      }
-      __syncthreads();
-    }
     // B: column masks inside the chunk: bit i of candidate j's 256-bit column = alive i < j
     //    suppresses j.  The four threads of a candidate take the earlier candidates i == g (mod 4):
     //    every lane of a warp then runs about the same number of tests (j / 4 of them; with one
@@ -431,7 +411,7 @@ proposals_kernel(const PropParams p) {
       unsigned res[CHUNK / 32];
 #pragma unroll
       for (int wd = 0; wd < CHUNK / 32; ++wd) res[wd] = 0u;
-      const bool alive_j = (s_alive[j >> 5] >> (j & 31)) & 1u;
+      const bool alive_j = (alivep[j >> 5] >> (j & 31)) & 1u;
       if (alive_j) {
         const float4 bj = s_cbox[j];
         const float aj = s_carea[j];
@@ -439,7 +419,7 @@ proposals_kernel(const PropParams p) {
 #pragma unroll
         for (int wd = 0; wd < CHUNK / 32; ++wd) {
           if (32 * wd < j) {
-            unsigned aw = s_alive[wd] & mine;
+            unsigned aw = alivep[wd] & mine;
             if (j - 32 * wd < 32) aw &= (1u << (j - 32 * wd)) - 1u;   // earlier candidates only
             while (aw) {
               const int bit = __ffs((int)aw) - 1;
@@ -459,9 +439,88 @@ proposals_kernel(const PropParams p) {
 #pragma unroll
       for (int wd = 0; wd < CHUNK / 32; wd += 2)
         if ((wd >> 1) == g) { lo = res[wd]; hi = res[wd + 1]; }
-      s_col[j * 4 + g] = ((unsigned long long)hi << 32) | lo;
+      colp[j * 4 + g] = ((unsigned long long)hi << 32) | lo;
     }
     __syncthreads();
+    } else {
+      // Cluster rounds: CTA r owns the candidates [r*Q, (r+1)*Q) of the chunk, TPC = 4*CS threads
+      // each.  A: the kept list, strided over the TPC threads.  B: the candidate's column over
+      // ALL earlier candidates i == sub (mod TPC) -- the alive bits of candidates owned by peers
+      // are not known yet, and columns are only ever ANDed with kept masks, so testing dead ones
+      // costs work, not correctness -- OR-reduced with shuffles.  Then ONE exchange per round:
+      // every CTA stores its alive words and its columns into every CTA's copy (distributed
+      // shared memory, two slot sets so that a CTA one round ahead cannot overwrite what a peer
+      // still reads) and the cluster barrier publishes them; C and D run redundantly.
+      constexpr int Q = CHUNK / CS, TPC = PT / Q, AW = (Q + 31) / 32;
+      static_assert(TPC <= 32 && Q * TPC == PT && Q >= 32, "4*CS threads per candidate, CS <= 8");
+      cg::cluster_group cluster = cg::this_cluster();
+      const int jl = tid / TPC, sub = tid % TPC;
+      const int j = crank * Q + jl;
+      int sup = 0;
+      float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+      float aj = 0.f;
+      if (j < nc) {
+        bj = s_cbox[j];
+        aj = s_carea[j];
+        for (int k = sub; k < nkept; k += TPC) {
+          if (iou_ge(s_kbox[k], s_karea[k], bj, aj, p.thr_ge)) { sup = 1; break; }
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < TPC; o <<= 1) sup |= __shfl_xor_sync(0xffffffffu, sup, o);
+      const bool alive_j = !sup && j < nc;
+      unsigned res[CHUNK / 32];
+#pragma unroll
+      for (int wd = 0; wd < CHUNK / 32; ++wd) res[wd] = 0u;
+      if (alive_j) {
+        // bits b of a word with (32*wd + b) % TPC == sub (32 % TPC == 0)
+        const unsigned mine = (TPC == 8 ? 0x01010101u : (TPC == 16 ? 0x00010001u : 1u)) << sub;
+#pragma unroll
+        for (int wd = 0; wd < CHUNK / 32; ++wd) {
+          if (32 * wd < j) {
+            unsigned aw = mine;
+            if (j - 32 * wd < 32) aw &= (1u << (j - 32 * wd)) - 1u;   // earlier candidates only
+            while (aw) {
+              const int bit = __ffs((int)aw) - 1;
+              aw &= aw - 1;
+              const int i = 32 * wd + bit;
+              if (iou_ge(s_cbox[i], s_carea[i], bj, aj, p.thr_ge)) res[wd] |= 1u << bit;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int wd = 0; wd < CHUNK / 32; ++wd) {
+#pragma unroll
+        for (int o = 1; o < TPC; o <<= 1) res[wd] |= __shfl_xor_sync(0xffffffffu, res[wd], o);
+      }
+      // alive bits of my Q candidates: one byte / halfword / word per warp (32 / TPC candidates)
+      {
+        const unsigned bal = __ballot_sync(0xffffffffu, alive_j && sub == 0);
+        if (lane == 0) {
+          unsigned bits = 0;
+#pragma unroll
+          for (int q = 0; q < 32 / TPC; ++q) bits |= ((bal >> (TPC * q)) & 1u) << q;
+          // warp w holds candidates jl in [w * 32/TPC, (w+1) * 32/TPC)
+          atomicOr(&s_sup[(warp * (32 / TPC)) >> 5], bits << ((warp * (32 / TPC)) & 31));
+        }
+      }
+      const int set = round & 1;
+      if (alive_j && sub < CS) {                      // my column into CTA `sub`'s copy
+        uint4* remote = reinterpret_cast<uint4*>(cluster.map_shared_rank(s_col, sub) +
+                                                 (size_t)set * CHUNK * 4 + (size_t)j * 4);
+        remote[0] = make_uint4(res[0], res[1], res[2], res[3]);
+        remote[1] = make_uint4(res[4], res[5], res[6], res[7]);
+      }
+      __syncthreads();                                // s_sup complete
+      if (tid < CS * AW) {                            // my alive words into every CTA's copy
+        const int peer = tid / AW, w = tid % AW;
+        unsigned* remote = cluster.map_shared_rank(s_alive, peer);
+        remote[set * (CHUNK / 32) + crank * AW + w] = s_sup[w];
+      }
+      cluster.sync();
+      if (tid < AW) s_sup[tid] = 0u;                  // for the next round (read after 2 barriers)
+    }
     // C: warp 0 resolves the chunk, 32 candidates at a time
     if (warp == 0) {
       unsigned kw[CHUNK / 32];
@@ -470,9 +529,9 @@ proposals_kernel(const PropParams p) {
 #pragma unroll
       for (int sb = 0; sb < CHUNK / 32; ++sb) {
         const int j = 32 * sb + lane;
-        const bool alive_j = (s_alive[sb] >> lane) & 1u;
-        const unsigned long long c0w = s_col[j * 4 + 0], c1w = s_col[j * 4 + 1];
-        const unsigned long long c2w = s_col[j * 4 + 2], c3w = s_col[j * 4 + 3];
+        const bool alive_j = (alivep[sb] >> lane) & 1u;
+        const unsigned long long c0w = colp[j * 4 + 0], c1w = colp[j * 4 + 1];
+        const unsigned long long c2w = colp[j * 4 + 2], c3w = colp[j * 4 + 3];
         const unsigned colw[8] = {(unsigned)c0w, (unsigned)(c0w >> 32), (unsigned)c1w,
                                   (unsigned)(c1w >> 32), (unsigned)c2w, (unsigned)(c2w >> 32),
                                   (unsigned)c3w, (unsigned)(c3w >> 32)};
@@ -549,9 +608,9 @@ size_t prop_smem_bytes(int NA, int kpad, int post) {
   size_t total = sizeof(unsigned long long) * (size_t)kpad;          // s_sort
   total += sizeof(unsigned) * (256 + 4) + sizeof(int) * 4;           // s_hist, s_bcast, s_cnt
   total += sizeof(unsigned) * na_pad;                                // score keys
-  total += sizeof(float4) * CHUNK + sizeof(unsigned long long) * CHUNK * 4 +
+  total += sizeof(float4) * CHUNK + sizeof(unsigned long long) * CHUNK * 4 * 2 +
            sizeof(float) * CHUNK + sizeof(int) * CHUNK + sizeof(unsigned) * CHUNK +
-           sizeof(unsigned) * (CHUNK / 32) * 2;                      // per-chunk NMS state
+           sizeof(unsigned) * (CHUNK / 32) * 3;                      // per-chunk NMS state
   total += (sizeof(float4) + sizeof(float)) * (size_t)post;          // kept list
   return total;
 }
@@ -606,25 +665,56 @@ int wssdl_proposals_impl(const float* cls_prob, const float* bbox_pred, const fl
   const size_t smem = prop_smem_bytes((int)NA, kpad, post_nms_topN);
   if (smem > smem_max) return WSSDL_ELIMIT;
   cudaStream_t s = to_cuda(stream);
-  // Small batches: a cluster of 8 CTAs per image (see the kernel); a batch that fills the
-  // machine by itself keeps one CTA per image.  Measured on B200 (B = 1: TRAIN 12000->2000
-  // 1.51 -> 0.62 ms, C2 2000->2000 0.52 -> 0.28 ms, TEST 6000->300 0.219 -> 0.210 ms; B = 16:
-  // TRAIN 1.61 -> 1.18 ms but TEST 0.22 -> 0.37 ms: with only 300 boxes to keep the split
-  // step is small and 16 clusters compete for GPC slots), hence: up to 4 images always, up to
-  // 18 images when the keep list is long.  WSSDL_PROPOSALS_CLUSTER=0|1 overrides.
-  constexpr int CSZ = 8;
+  // Batches that leave SMs idle: a cluster of 2 / 4 / 8 CTAs per image (see the kernel), the
+  // largest size whose B clusters are resident at once (cudaOccupancyMaxActiveClusters knows the
+  // GPC layout); a batch that fills the machine keeps one CTA per image.
+  // WSSDL_TUNE_PROPOSALS_CLUSTER: -1 by shape, 0 one CTA per image, 1 by shape (as -1), 2 / 4 / 8
+  // that cluster size.
+  auto set_smem = [&](auto kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  };
+  auto fits = [&](auto kernel, int cs) {
+    if ((long long)B * cs > WSSDL_NUM_SMS) return false;
+    if (set_smem(kernel) != cudaSuccess) return false;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * cs));
+    cfg.blockDim = dim3(PT);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+    return n >= B;
+  };
   const int ctune = wssdl_tuning(WSSDL_TUNE_PROPOSALS_CLUSTER);
-  const bool clustered = ctune >= 0 ? (ctune == 1)
-                              : ((long long)B * CSZ <= WSSDL_NUM_SMS &&
-                                 (B <= 4 || post_nms_topN >= 1024));
-  if (clustered)
-    WSSDL_RETURN_IF_CUDA(cudaFuncSetAttribute(proposals_kernel<CSZ>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem));
-  else
-    WSSDL_RETURN_IF_CUDA(cudaFuncSetAttribute(proposals_kernel<1>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem));
+  int cs = 1;
+  if (ctune == 2 || ctune == 4 || ctune == 8) {
+    cs = ctune;
+  } else if (ctune != 0) {
+    // (cached per (B, smem): the occupancy query is a driver call)
+    static std::mutex c_mu;
+    static int c_B = -1, c_cs = 1;
+    static size_t c_smem = 0;
+    std::lock_guard<std::mutex> lock(c_mu);
+    if (c_B == B && c_smem == smem) {
+      cs = c_cs;
+    } else {
+      if (fits(proposals_kernel<8>, 8)) cs = 8;
+      else if (fits(proposals_kernel<4>, 4)) cs = 4;
+      else if (fits(proposals_kernel<2>, 2)) cs = 2;
+      c_B = B; c_smem = smem; c_cs = cs;
+    }
+  }
+  if (cs == 8) WSSDL_RETURN_IF_CUDA(set_smem(proposals_kernel<8>));
+  else if (cs == 4) WSSDL_RETURN_IF_CUDA(set_smem(proposals_kernel<4>));
+  else if (cs == 2) WSSDL_RETURN_IF_CUDA(set_smem(proposals_kernel<2>));
+  else WSSDL_RETURN_IF_CUDA(set_smem(proposals_kernel<1>));
   PropParams p;
   p.cls_prob = cls_prob; p.bbox_pred = bbox_pred; p.im_info = im_info;
   p.info_stride = info_stride; p.H = H; p.W = W; p.A = A; p.NA = (int)NA;
@@ -642,20 +732,22 @@ int wssdl_proposals_impl(const float* cls_prob, const float* bbox_pred, const fl
   p.decoded = decoded;
   // base anchors: HOST pointer (generate_anchors runs on the host, as in the reference)
   for (int i = 0; i < MAX_ANCHORS * 4; ++i) p.base[i] = i < 4 * A ? base_anchors[i] : 0.f;
-  if (clustered) {
+  if (cs > 1) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(B * CSZ));
+    cfg.gridDim = dim3((unsigned)(B * cs));
     cfg.blockDim = dim3(PT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CSZ;
+    attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    WSSDL_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, proposals_kernel<CSZ>, p));
+    if (cs == 8) WSSDL_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, proposals_kernel<8>, p));
+    else if (cs == 4) WSSDL_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, proposals_kernel<4>, p));
+    else WSSDL_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, proposals_kernel<2>, p));
   } else {
     proposals_kernel<1><<<B, PT, smem, s>>>(p);
   }

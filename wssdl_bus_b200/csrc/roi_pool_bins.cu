@@ -77,6 +77,12 @@ __device__ __forceinline__ void tma_prefetch_band(const CUtensorMap* tmap, int c
                : "memory");
 }
 
+// programmatic dependent launch (no-ops in a kernel launched without the attribute)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ int edge_lo(int mode, int p, float bin) {
   const float v = __fmul_rn((float)p, bin);
   return mode == WSSDL_BIN_CPU_TRUNC ? (int)v : (int)floorf(v);   // cc:167-170 / gpu.cu.cc:51-58
@@ -297,7 +303,7 @@ struct SortArgs {
   int rch;              // RoIs whose geometry is resident at a time
   int stride;           // > 0: image-major RoIs, image b owns rows [b*stride, (b+1)*stride)
   BandGeom bg;
-  FastDiv divPH, divStep;
+  FastDiv divPH, divStep, divPW, divPHPW;
 };
 
 __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortArgs a) {
@@ -307,6 +313,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
   const int tid = threadIdx.x;
   const int H = a.H, W = a.W, PH = a.PH, PW = a.PW, NB = a.bg.NB;
   const int img = blockIdx.x;                       // == B: RoIs with no valid image
+  // the pooling kernel may become resident (and stage its bands) now; this kernel itself may
+  // have been launched the same way behind the kernel that writes the RoIs
+  griddep_launch_dependents();
+  griddep_wait();
   const bool valid_img = img < a.B;
   const int mode = a.bin_mode;
 
@@ -439,36 +449,40 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
       geometry(c0, nb);
       __syncthreads();
     }
-    for (int t = tid; t < nb * PH; t += S_THREADS) {
-      const int rl = (int)fastdiv((unsigned)t, a.divPH);
-      const int ph = t - rl * PH;
-      const Row r = row_of(rl, ph);
-      const unsigned obin = (unsigned)(s_nb[rl] + ph * PW);
-      if (r.nh <= 0) {
-        const int pos = atomicAdd(&s_cur[r.band][CLS_EMPTY], PW);
-        for (int pw = 0; pw < PW; ++pw) {
-          recs[pos + pw] = make_uint2(obin + pw, (unsigned)CLS_EMPTY << 12);
-        }
-        continue;
+    // one thread per bin (per (RoI, ph) row and class the loops were 60 % of this kernel, most
+    // of their iterations skipping): the lanes of a warp that hold bins of the same (band, class)
+    // take their slots with ONE shared-memory atomic, in lane order -- the bins of a row that
+    // share a class stay next to each other, so a warp's output rows stay contiguous
+    const int nbins = nb * PH * PW;
+    for (int t0 = 0; t0 < nbins; t0 += S_THREADS) {
+      const int t = t0 + tid;
+      const bool act = t < nbins;
+      int key = -1 - (tid & 31);                    // idle lanes: a key of their own
+      unsigned recx = 0, recy = 0;
+      if (act) {
+        const int rl = (int)fastdiv((unsigned)t, a.divPHPW);
+        const int rem = t - rl * PH * PW;
+        const int ph = (int)fastdiv((unsigned)rem, a.divPW);
+        const int pw = rem - ph * PW;
+        const Row r = row_of(rl, ph);
+        const unsigned e = s_we[rl * PW + pw];
+        const int nw = (int)(e >> 8);
+        int cls;
+        if (r.nh <= 0 || nw == 0) cls = CLS_EMPTY;
+        else if (r.slow) cls = CLS_SLOW;
+        else cls = (min(r.nh, N_DIM) - 1) * N_DIM - 1 + min(nw, N_DIM);
+        key = r.band * N_CLS + cls;
+        const unsigned cell =
+            cls < CLS_EMPTY ? (unsigned)((r.hs - r.band * a.bg.step) * W + (int)(e & 255u)) : 0u;
+        recx = (unsigned)(s_nb[rl] + rem);
+        recy = cell | ((unsigned)cls << 12);
       }
-      const int crow = (min(r.nh, N_DIM) - 1) * N_DIM - 1;
-      const int cell_row = (r.hs - r.band * a.bg.step) * W;
-      const unsigned short* we_p = s_we + rl * PW;
-      const unsigned long long wf = s_wf[rl];
-#pragma unroll 1
-      for (int k = 0; k <= N_DIM; ++k) {
-        const int cnt = (int)((wf >> (7 * k)) & 127u);
-        if (!cnt) continue;
-        const int cls = k == 0 ? CLS_EMPTY : (r.slow ? CLS_SLOW : crow + k);
-        int pos = atomicAdd(&s_cur[r.band][cls], cnt);
-        for (int pw = 0; pw < PW; ++pw) {
-          const unsigned e = we_p[pw];
-          if (min((int)(e >> 8), N_DIM) != k) continue;
-          const unsigned cell = (cls < CLS_EMPTY) ? (unsigned)(cell_row + (int)(e & 255u)) : 0u;
-          recs[pos] = make_uint2(obin + pw, cell | ((unsigned)cls << 12));
-          ++pos;
-        }
-      }
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      const int leader = __ffs((int)peers) - 1;
+      int base = 0;
+      if (act && (tid & 31) == leader) base = atomicAdd(&(&s_cur[0][0])[key], __popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (act) recs[base + __popc(peers & ((1u << (tid & 31)) - 1u))] = make_uint2(recx, recy);
     }
   }
   if (tid < NB_MAX * N_CLS) {
@@ -541,10 +555,6 @@ roi_pool_fwd_bins_kernel(const __grid_constant__ CUtensorMap tmap, const PoolArg
   const bool valid_img = img < a.B;
 
   if (!valid_img && band != 0) return;              // their (empty) bins all sit in band 0
-  const int4 tb = a.table[img * NB_MAX + band];
-  const int g_begin = (int)((long long)tb.y * chunk / a.nchunks);
-  const int g_count = (int)((long long)tb.y * (chunk + 1) / a.nchunks) - g_begin;
-  if (g_count <= 0) return;
   const int row0 = band * a.bg.step;                // first resident row
   const int row1 = min(row0 + a.bg.Hb, H);          // one past the last resident row
   const int slice_begin = blockIdx.x * a.sg;
@@ -593,6 +603,18 @@ roi_pool_fwd_bins_kernel(const __grid_constant__ CUtensorMap tmap, const PoolArg
       __syncthreads();
     }
   };
+  // The band does not depend on the pre-pass: its copy is in flight before this kernel waits
+  // for the bin-sort kernel (programmatic dependent launch: the CTAs of the first wave are
+  // resident, barriers initialised and bands staged while the pre-pass still runs).
+  stage(slice_begin);
+  griddep_wait();
+  const int4 tb = a.table[img * NB_MAX + band];
+  const int g_begin = (int)((long long)tb.y * chunk / a.nchunks);
+  const int g_count = (int)((long long)tb.y * (chunk + 1) / a.nchunks) - g_begin;
+  if (g_count <= 0) {
+    stage_wait();                                   // (no exit with a copy into this CTA in flight)
+    return;
+  }
   // the records of groups [gb, gb + n) of this CTA's range: one bulk copy
   const uint2* const recs_cta = a.recs + (size_t)(tb.x + g_begin) * 8;
   auto stage_recs = [&](int gb, int n) {
@@ -602,7 +624,6 @@ roi_pool_fwd_bins_kernel(const __grid_constant__ CUtensorMap tmap, const PoolArg
     }
   };
   const int cap_g = a.rec_cap >> 3;
-  stage(slice_begin);
   stage_recs(0, min(cap_g, g_count));
 
   // opaque unit operands of the conditional moves (see the tiled kernel in roi_pool.cu)
@@ -874,6 +895,7 @@ cudaError_t wssdl_roi::launch_fwd_bins(const BinsPlan& p, const float* bottom, c
                                        int B, int H, int W, int C, int R, int PH, int PW,
                                        float spatial_scale, int bin_mode, float* top, int* argmax,
                                        void* workspace, cudaStream_t s, int grouped_stride) {
+  const bool pdl = wssdl_tuning(WSSDL_TUNE_PDL) != 0;
   int* img_start = nullptr;
   int* perm = nullptr;
   if (grouped_stride > 0 && (long long)grouped_stride * B != R) return cudaErrorInvalidValue;
@@ -896,12 +918,27 @@ cudaError_t wssdl_roi::launch_fwd_bins(const BinsPlan& p, const float* bottom, c
   sa.bg = p.g;
   sa.divPH = make_fastdiv((unsigned)PH);
   sa.divStep = make_fastdiv((unsigned)p.g.step);
+  sa.divPW = make_fastdiv((unsigned)PW);
+  sa.divPHPW = make_fastdiv((unsigned)(PH * PW));
   if (p.sort_smem > 48 * 1024) {                    // beyond the default carve-out: opt in
     cudaError_t e = cudaFuncSetAttribute(roi_bin_sort_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.sort_smem);
     if (e != cudaSuccess) return e;
   }
-  roi_bin_sort_kernel<<<B + 1, S_THREADS, p.sort_smem, s>>>(sa);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B + 1));
+    cfg.blockDim = dim3(S_THREADS);
+    cfg.dynamicSmemBytes = p.sort_smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, roi_bin_sort_kernel, sa);
+    if (e != cudaSuccess) return e;
+  }
   // ---- tensor map of the map as (C, W, H, B), box = (32 channels, W, Hb rows, 1 image)
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
@@ -937,7 +974,18 @@ cudaError_t wssdl_roi::launch_fwd_bins(const BinsPlan& p, const float* bottom, c
     static unsigned long long done_k = 0;                                                     \
     cudaError_t e = allow_big_smem(roi_pool_fwd_bins_kernel<NT, A, L, T>, &done_k);           \
     if (e != cudaSuccess) return e;                                                           \
-    roi_pool_fwd_bins_kernel<NT, A, L, T><<<grid, NT, p.smem, s>>>(tmap, a);                  \
+    cudaLaunchConfig_t cfg = {};                                                              \
+    cfg.gridDim = grid;                                                                       \
+    cfg.blockDim = dim3(NT);                                                                  \
+    cfg.dynamicSmemBytes = p.smem;                                                            \
+    cfg.stream = s;                                                                           \
+    cudaLaunchAttribute attr[1];                                                              \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                          \
+    attr[0].val.programmaticStreamSerializationAllowed = 1;                                   \
+    cfg.attrs = attr;                                                                         \
+    cfg.numAttrs = pdl ? 1 : 0;                                                               \
+    e = cudaLaunchKernelEx(&cfg, roi_pool_fwd_bins_kernel<NT, A, L, T>, tmap, a);             \
+    if (e != cudaSuccess) return e;                                                           \
   } while (0)
 #define LAUNCH_BINS_T(NT, A, L)                                                               \
   do {                                                                                        \
