@@ -882,7 +882,11 @@ BinsPlan wssdl_roi::plan_bins(int B, int H, int W, int C, int R, int PH, int PW,
     if (nch > 1 && (double)R / nimg * PH * PW / p.g.NB / nch < 8.0 * (p.threads / 32)) break;
     if ((long long)p.g.NB * nch > 65535) break;
     const long long ctas = (long long)n_slices * p.g.NB * nch * nimg;
-    const double t_cta = 1.0 + 2.5 / per_sm + work_us / nch;
+    // (the quadratic term: the 16 slice CTAs of a band drift apart the longer they run, and the
+    // 2 KB output rows they share then reach DRAM in pieces -- measured on C4, 256 images:
+    // 3.14 / 3.03 / 3.21 ms with 1 / 2 / 3 ranges per band, 32 images: 0.428 / 0.412 / 0.430)
+    const double w_cta = work_us / nch;
+    const double t_cta = 1.0 + 2.5 / per_sm + w_cta + 0.004 * w_cta * w_cta;
     const double waves = (double)((ctas + WSSDL_NUM_SMS * per_sm - 1) / (WSSDL_NUM_SMS * per_sm));
     const double t = waves * t_cta;
     if (t < best * 0.999) { best = t; p.nchunks = nch; }
