@@ -369,8 +369,8 @@ int wssdl_roi_pool_fwd_grouped(const float* bottom, const float* rois, int roi_s
  *            (philox4x32-10(counter (rank, i, 2 fg / 3 bg, 0), key seed).x, rank), in that order.
  *            Image i owns output rows [i*rois_per_image, (i+1)*rois_per_image); rows past
  *            fg_this + bg_this are zero; out_counts [B_supervised,2] = (fg_this, bg_this).
- * Limits: max_gt <= 64; 2*(R+max_gt) (+ rois_per_image + R + max_gt with Philox) ints of shared
- * memory <= 200 KB, else WSSDL_ELIMIT. */
+ * Limits: max_gt <= 64; with Philox rois_per_image + R + max_gt ints of shared memory <= 200 KB,
+ * else WSSDL_ELIMIT. */
 size_t wssdl_roi_targets_workspace_bytes(int B_supervised, int R, int max_gt);
 
 int wssdl_roi_match(const float* rois, int R, const float* gt_boxes, const int* num_gt,

@@ -212,33 +212,66 @@ def main():
                     t0 = time.perf_counter()
                     fn(bn, qn)
                     emit(out, op="cpu_bbox_overlaps", N=n, K=k, ms=(time.perf_counter() - t0) * 1e3)
+    if want("chain"):
+        # BASELINE config C1: the single-image chain proposals -> RoI pooling, the latency a
+        # serving loop sees per image.  Three ways to issue the same three kernels: the two
+        # public ops back to back, the fused entry (one host call, PDL between the kernels), and
+        # the fused entry captured once in a CUDA graph and replayed.
+        for B in (1, 2, 4):
+            feat = torch.from_numpy(syn.feature_map(1, B, 38, 50, 512)).cuda()
+            cls, reg, info = [torch.from_numpy(v).cuda() for v in syn.rpn_outputs(7, B, 38, 50, 9)]
+            hot = HotPath()
+            for tag, fn in (("two ops", lambda: hot.run(feat, cls, reg, info, fused=False)),
+                            ("fused entry", lambda: hot.run(feat, cls, reg, info))):
+                med, best = timeit(fn, iters=30, flush=False)
+                emit(out, op="c1_chain", tag=tag, B=B, ms=med, ms_min=best)
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    hot.run(feat, cls, reg, info)
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                res = hot.run(feat, cls, reg, info)
+            eager = hot.run(feat, cls, reg, info)
+            g.replay()
+            torch.cuda.synchronize()
+            same = bool(torch.equal(res["top"], eager["top"]) and torch.equal(res["rois"], eager["rois"]))
+            med, best = timeit(g.replay, iters=30, flush=False)
+            emit(out, op="c1_chain", tag="fused entry, CUDA graph replay", B=B, ms=med, ms_min=best,
+                 equals_eager=same)
     if want("train"):
         # BASELINE config C2: the device kernels of one training step, chained on one stream
-        # with no host synchronisation (anchor labels -> proposals 2000 pre-NMS -> RoI x GT IoU
-        # -> 128 RoIs per image -> roi_pool fwd + bwd).  The reference's npr.choice sampling
-        # stays on the host in the product path; here the first 128 proposals stand in for it.
+        # with NO host synchronisation: anchor-target layer (labels + Philox subsampling +
+        # targets) -> proposals 12000 -> 2000 -> proposal-target layer (RoI x GT matching, Philox
+        # sampling of 128 RoIs per image, targets) -> roi_pool fwd + bwd on the sampled RoIs.
+        from wssdl_bus_b200.rpn_msr import anchor_target_layer_tf_bus as atl
+        from wssdl_bus_b200.rpn_msr import proposal_target_layer_tf_bus as ptl
         from wssdl_bus_b200.rpn_msr.generate_anchors import generate_anchors
         base = generate_anchors()
         for B in (1, 16):
             feat = torch.from_numpy(syn.feature_map(1, B, 38, 50, 512)).cuda()
             cls, reg, info = [torch.from_numpy(v).cuda() for v in syn.rpn_outputs(7, B, 38, 50, 9)]
             gt, num = [torch.from_numpy(v).cuda() for v in syn.gt_boxes(9, B)]
-            gt64 = gt[:, :, :4].double().contiguous()
+            num = num.int()
+            score = torch.zeros((B, 38, 50, 18), device="cuda")
             gtop = torch.randn((B * 128, 7, 7, 512), device="cuda")
-            pick = (torch.arange(B, device="cuda")[:, None] * 2000 + torch.arange(128, device="cuda")[None]).reshape(-1)
 
             def step():
-                ops.anchor_labels(gt, num, info, 38, 50, base, 16)
-                p = ops.proposals(cls, reg, info, base, 16, 2000, 2000, 0.7, 16)
-                r = p["rois"]
-                for b in range(B):
-                    ops.bbox_overlaps_device(r[b * 2000:(b + 1) * 2000, 1:5].double(), gt64[b], ops.IOU, torch.float64)
-                rr = r[pick].contiguous()
+                atl.anchor_target_layer(score, gt, num, info, None, [16, ], [8, 16, 32], "SNUBH",
+                                        sampler="philox", seed=1, return_device=True)
+                p = ops.proposals(cls, reg, info, base, 16, 12000, 2000, 0.7, 16)
+                out_ = ptl.proposal_target_layer(p["rois"], gt, num, 3, True, False, sampler="philox",
+                                                 seed=2, return_device=True)
+                rr = out_[0]
                 top, arg = ops.roi_pool_forward(feat, rr, 7, 7, 1 / 16.)
                 ops.roi_pool_backward((B, 38, 50, 512), rr, arg, gtop, 7, 7, 1 / 16.)
-            med, best = timeit(step, iters=10, flush=False)
-            emit(out, op="train_step_device_kernels", tag="C2 2000 pre-NMS, 128 RoIs/image, fwd+bwd", B=B,
-                 ms=med, ms_min=best, images_per_s=B / med * 1e3)
+            with torch.autograd.profiler.profile(enabled=False):
+                med, best = timeit(step, iters=10, flush=False)
+            emit(out, op="train_step_device_kernels",
+                 tag="C2: anchor targets + proposals 12000->2000 + proposal targets (Philox, no D2H) + "
+                     "roi_pool fwd+bwd on 128 RoIs/image", B=B, ms=med, ms_min=best,
+                 images_per_s=B / med * 1e3)
     if want("detect"):
         for B in (1, 256):
             S, K = 300, 3

@@ -275,7 +275,8 @@ struct RmParams {
   double fg_thresh, bg_hi, bg_lo;
   int* cand;                 // [Bs,cap]  RoI row (>= 0) or -(g+1) for GT row g
   int* assign;               // [Bs,cap]  first argmax over the fg GT rows
-  int* rank;                 // [Bs,cap]  rank among fg candidates | 0x40000000 ; among bg | 0x20000000 ; -1
+  int* fg_list;              // [Bs,cap]  candidate slot of the fg candidate of rank r
+  int* bg_list;              // [Bs,cap]  the same for the bg candidates
   int* counts;               // [Bs,4]    candidates, fg candidates, bg candidates, fg GT rows
 };
 
@@ -296,7 +297,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) roi_match_kernel(const RmParams
   for (int i = tid; i < npos * 4; i += PT_THREADS) s_gt[i >> 2][i & 3] = (double)gt[(i >> 2) * 5 + (i & 3)];
   int* cand = p.cand + (size_t)img * p.cap;
   int* assign = p.assign + (size_t)img * p.cap;
-  int* rank = p.rank + (size_t)img * p.cap;
+  int* fg_list = p.fg_list + (size_t)img * p.cap;
+  int* bg_list = p.bg_list + (size_t)img * p.cap;
   // ---- candidates: the RoIs of this image in their original order, then the fg GT rows
   int ncand = 0;
   for (int r0 = 0; r0 < p.R; r0 += PT_THREADS) {
@@ -363,8 +365,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) roi_match_kernel(const RmParams
     }
     if (c < ncand) {
       const unsigned lt = (1u << lane) - 1u;
-      rank[c] = is_fg ? (0x40000000 | (fg_total + f_before + __popc(bf & lt)))
-                      : (is_bg ? (0x20000000 | (bg_total + b_before + __popc(bb & lt))) : -1);
+      if (is_fg) fg_list[fg_total + f_before + __popc(bf & lt)] = c;
+      if (is_bg) bg_list[bg_total + b_before + __popc(bb & lt)] = c;
     }
     fg_total += f_tot;
     bg_total += b_tot;
@@ -382,7 +384,8 @@ struct RtParams {
   int max_gt, cap, K;
   const int* cand;
   const int* assign;
-  const int* rank;
+  const int* fg_list;
+  const int* bg_list;
   const int* counts;         // [Bs,4] from roi_match_kernel
   int mode;
   const int* sel;            // RANKS mode: per image fg ranks in selection order, then bg ranks
@@ -405,17 +408,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) roi_targets_kernel(const RtPara
   extern __shared__ __align__(16) unsigned char rt_smem[];
   const int img = blockIdx.x, tid = threadIdx.x;
   const int ncand = p.counts[4 * img], n_fg = p.counts[4 * img + 1], n_bg = p.counts[4 * img + 2];
-  int* s_fg = reinterpret_cast<int*>(rt_smem);      // [cap] candidate slot of fg rank r
-  int* s_bg = s_fg + p.cap;                         // [cap] candidate slot of bg rank r
-  int* s_sel = s_bg + p.cap;                        // [rois_per_image] (PHILOX) selected slots, in order
+  int* s_sel = reinterpret_cast<int*>(rt_smem);     // [rois_per_image] (PHILOX) selected slots, in order
   const int* cand = p.cand + (size_t)img * p.cap;
   const int* assign = p.assign + (size_t)img * p.cap;
-  const int* rank = p.rank + (size_t)img * p.cap;
-  for (int c = tid; c < ncand; c += PT_THREADS) {
-    const int r = rank[c];
-    if (r >= 0) { if (r & 0x40000000) s_fg[r & 0x1fffffff] = c; else s_bg[r & 0x1fffffff] = c; }
-  }
-  __syncthreads();
+  const int* fg_of = p.fg_list + (size_t)img * p.cap;   // candidate slot of fg rank r (global memory)
+  const int* bg_of = p.bg_list + (size_t)img * p.cap;
+  (void)ncand;
   int fg_this, bg_this, row0;
   if (p.mode == WSSDL_SAMPLE_RANKS) {
     fg_this = p.sel_off[2 * img + 1] - p.sel_off[2 * img];
@@ -443,7 +441,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) roi_targets_kernel(const RtPara
           const unsigned other = s_key[q];
           before += (other < mine) || (other == mine && q < r);
         }
-        if (before < k) s_sel[base + before] = which == 0 ? s_fg[r] : s_bg[r];
+        if (before < k) s_sel[base + before] = which == 0 ? fg_of[r] : bg_of[r];
       }
     }
     __syncthreads();
@@ -456,7 +454,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) roi_targets_kernel(const RtPara
     int c;
     if (p.mode == WSSDL_SAMPLE_RANKS) {
       const int rk = p.sel[p.sel_off[2 * img] + j];
-      c = j < fg_this ? s_fg[rk] : s_bg[rk];
+      c = j < fg_this ? fg_of[rk] : bg_of[rk];
     } else {
       c = s_sel[j];
     }
@@ -557,10 +555,10 @@ extern "C" int wssdl_anchor_targets(const float* labels_pre, const int* argmax_g
 extern "C" size_t wssdl_roi_targets_workspace_bytes(int B_supervised, int R, int max_gt) {
   if (B_supervised <= 0 || R < 0 || max_gt < 0) return 256;
   const size_t cap = (size_t)R + (size_t)max_gt;
-  return sizeof(int) * ((size_t)B_supervised * cap * 3 + (size_t)B_supervised * 4) + 256;
+  return sizeof(int) * ((size_t)B_supervised * cap * 4 + (size_t)B_supervised * 4) + 256;
 }
 
-// workspace: cand | assign | rank [Bs,cap] each, counts [Bs,4]
+// workspace: cand | assign | fg_list | bg_list, [Bs,cap] each
 extern "C" int wssdl_roi_match(const float* rois, int R, const float* gt_boxes, const int* num_gt,
                                int max_gt, int B_supervised, int add_gt, double fg_thresh,
                                double bg_thresh_hi, double bg_thresh_lo, void* workspace,
@@ -576,7 +574,9 @@ extern "C" int wssdl_roi_match(const float* rois, int R, const float* gt_boxes, 
   p.cap = R + max_gt;
   p.fg_thresh = fg_thresh; p.bg_hi = bg_thresh_hi; p.bg_lo = bg_thresh_lo;
   int* w = static_cast<int*>(workspace);
-  p.cand = w; p.assign = w + (size_t)B_supervised * p.cap; p.rank = p.assign + (size_t)B_supervised * p.cap;
+  p.cand = w; p.assign = w + (size_t)B_supervised * p.cap;
+  p.fg_list = p.assign + (size_t)B_supervised * p.cap;
+  p.bg_list = p.fg_list + (size_t)B_supervised * p.cap;
   p.counts = counts;
   roi_match_kernel<<<B_supervised, PT_THREADS, 0, to_cuda(stream)>>>(p);
   WSSDL_CHECK_LAUNCH();
@@ -603,7 +603,9 @@ extern "C" int wssdl_roi_targets(const float* rois, int R, const float* gt_boxes
   RtParams p;
   p.rois = rois; p.gt_boxes = gt_boxes; p.max_gt = max_gt; p.cap = R + max_gt; p.K = num_classes;
   const int* w = static_cast<const int*>(workspace);
-  p.cand = w; p.assign = w + (size_t)B_supervised * p.cap; p.rank = p.assign + (size_t)B_supervised * p.cap;
+  p.cand = w; p.assign = w + (size_t)B_supervised * p.cap;
+  p.fg_list = p.assign + (size_t)B_supervised * p.cap;
+  p.bg_list = p.fg_list + (size_t)B_supervised * p.cap;
   p.counts = counts;
   p.mode = sample_mode; p.sel = sel; p.sel_off = sel_off; p.row_off = row_off;
   p.fg_quota = fg_rois_per_image; p.rois_per_image = rois_per_image; p.seed = seed;
@@ -615,8 +617,8 @@ extern "C" int wssdl_roi_targets(const float* rois, int R, const float* gt_boxes
   }
   p.out_rois = out_rois; p.out_labels = out_labels; p.out_targets = out_targets;
   p.out_inside = out_inside; p.out_outside = out_outside; p.out_counts = out_counts;
-  const size_t smem = sizeof(int) * ((size_t)2 * p.cap +
-                                     (sample_mode == WSSDL_SAMPLE_PHILOX ? (size_t)rois_per_image + p.cap : 0));
+  const size_t smem = sample_mode == WSSDL_SAMPLE_PHILOX
+                          ? sizeof(int) * ((size_t)rois_per_image + p.cap) : 16;
   if (smem > 200 * 1024) return WSSDL_ELIMIT;
   if (smem > 48 * 1024)
     WSSDL_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_targets_kernel,
