@@ -277,7 +277,8 @@ __device__ __forceinline__ void pool_rows_any(Acc& a, unsigned q, int key, int n
 // (trailing)}.
 constexpr int S_THREADS = 1024;
 constexpr int NB_MAX = 4;
-constexpr int PAD_PER_IMAGE = NB_MAX * N_CLS * 8 + 8;
+constexpr int PAD_PER_IMAGE = NB_MAX * N_CLS * 8 + 8;   // per (image, sub-list)
+constexpr int S_MAX = 4;                // sub-lists per image (sort CTAs per image)
 constexpr unsigned RECY_PAD = 1u << 11;
 
 // special = pooled by the general per-lane code of the pooling kernel
@@ -302,6 +303,8 @@ struct SortArgs {
   int bin_mode;
   int rch;              // RoIs whose geometry is resident at a time
   int stride;           // > 0: image-major RoIs, image b owns rows [b*stride, (b+1)*stride)
+  int nsub;             // CTAs per image: CTA (img, sub) sorts the sub-th part of the image's RoIs into
+                        // a list of its own (table entry (img, band, sub))
   BandGeom bg;
   FastDiv divPH, divStep, divPW, divPHPW;
 };
@@ -312,7 +315,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
   __shared__ int s_count, s_before;
   const int tid = threadIdx.x;
   const int H = a.H, W = a.W, PH = a.PH, PW = a.PW, NB = a.bg.NB;
-  const int img = blockIdx.x;                       // == B: RoIs with no valid image
+  const int img = blockIdx.x / a.nsub;              // == B: RoIs with no valid image
+  const int sub = blockIdx.x - img * a.nsub;
   // the pooling kernel may become resident (and stage its bands) now; this kernel itself may
   // have been launched the same way behind the kernel that writes the RoIs
   griddep_launch_dependents();
@@ -325,7 +329,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
   float* s_bh = reinterpret_cast<float*>(s_sh + a.rch);        // bin_h
   int* s_nb = reinterpret_cast<int*>(s_bh + a.rch);            // RoI index x PH*PW
   unsigned short* s_we = reinterpret_cast<unsigned short*>(s_nb + a.rch);   // ws | nw << 8
-  unsigned short* s_list = s_we + (((size_t)a.rch * PW + 7) & ~(size_t)7);  // scan mode only
+  unsigned* s_row = reinterpret_cast<unsigned*>(s_we + (((size_t)a.rch * PW + 7) & ~(size_t)7));  // [rch*PH]
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(s_row + (size_t)a.rch * PH);   // scan mode only
 
   // ---- this image's RoIs, and how many RoIs the images before it hold
   const int* list = nullptr;
@@ -352,11 +357,19 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
     before = s_before;
   }
   for (int i = tid; i < NB_MAX * N_CLS; i += S_THREADS) (&s_hist[0][0])[i] = 0;
+  {                                                 // this CTA's part of the image's RoIs
+    const int lo = (int)((long long)n_img * sub / a.nsub);
+    const int hi = (int)((long long)n_img * (sub + 1) / a.nsub);
+    before += lo;
+    if (list) list += lo;
+    n_img = hi - lo;
+  }
   if (n_img == 0) {
-    if (tid < NB_MAX) a.table[img * NB_MAX + tid] = make_int4(0, 0, 0, 0);
+    if (tid < NB_MAX) a.table[(img * NB_MAX + tid) * S_MAX + sub] = make_int4(0, 0, 0, 0);
     return;
   }
-  const size_t rec0 = (((size_t)before * PH * PW + 7) & ~(size_t)7) + (size_t)img * PAD_PER_IMAGE;
+  const size_t rec0 = (((size_t)before * PH * PW + 7) & ~(size_t)7) +
+                      (size_t)(img * a.nsub + sub) * PAD_PER_IMAGE;
 
   // RoI geometry with the reference's float expressions (cc:153-176); the width histogram of a
   // RoI's PW bins (9 fields of 7 bits: 0, 1..7, >= 8 cells) is shared by its PH rows
@@ -397,6 +410,12 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
     return r;
   };
 
+  // a (RoI, ph) row as one word for the per-bin pass: hs | min(nh, 8) << 16 | band << 20 | slow << 22
+  auto pack_row = [&](const Row& r) {
+    return (unsigned)r.hs | ((unsigned)min(max(r.nh, 0), N_DIM) << 16) | ((unsigned)r.band << 20) |
+           ((unsigned)(r.slow ? 1 : 0) << 22);
+  };
+
   // ---- pass A: class histogram per band
   for (int c0 = 0; c0 < n_img; c0 += a.rch) {
     const int nb = min(a.rch, n_img - c0);
@@ -407,6 +426,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
       const int rl = (int)fastdiv((unsigned)t, a.divPH);
       const int ph = t - rl * PH;
       const Row r = row_of(rl, ph);
+      s_row[t] = pack_row(r);
       if (r.nh <= 0) { atomicAdd(&s_hist[r.band][CLS_EMPTY], PW); continue; }
       const int crow = (min(r.nh, N_DIM) - 1) * N_DIM - 1;
       const unsigned long long wf = s_wf[rl];
@@ -436,7 +456,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
     s_start[b][c] = bands_before + before_c;
     s_cur[b][c] = bands_before + before_c;
     if (c == 0)
-      a.table[img * NB_MAX + b] = make_int4((int)((rec0 + bands_before) >> 3), band_total >> 3,
+      a.table[(img * NB_MAX + b) * S_MAX + sub] = make_int4((int)((rec0 + bands_before) >> 3), band_total >> 3,
                                             special >> 3, ((s_hist[b][CLS_EMPTY] + 7) & ~7) >> 3);
   }
   __syncthreads();
@@ -448,10 +468,15 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
       __syncthreads();
       geometry(c0, nb);
       __syncthreads();
+      for (int t = tid; t < nb * PH; t += S_THREADS) {
+        const int rl = (int)fastdiv((unsigned)t, a.divPH);
+        s_row[t] = pack_row(row_of(rl, t - rl * PH));
+      }
+      __syncthreads();
     }
     // one thread per bin (per (RoI, ph) row and class the loops were 60 % of this kernel, most
     // of their iterations skipping): the lanes of a warp that hold bins of the same (band, class)
-    // take their slots with ONE shared-memory atomic, in lane order -- the bins of a row that
+    // take their slots with ONE shared-memory atomic per run of adjacent lanes, in lane order -- the bins of a row that
     // share a class stay next to each other, so a warp's output rows stay contiguous
     const int nbins = nb * PH * PW;
     for (int t0 = 0; t0 < nbins; t0 += S_THREADS) {
@@ -464,25 +489,32 @@ __global__ void __launch_bounds__(S_THREADS, 1) roi_bin_sort_kernel(const SortAr
         const int rem = t - rl * PH * PW;
         const int ph = (int)fastdiv((unsigned)rem, a.divPW);
         const int pw = rem - ph * PW;
-        const Row r = row_of(rl, ph);
+        const unsigned rw = s_row[rl * PH + ph];
+        const int nh8 = (int)((rw >> 16) & 15u), band = (int)((rw >> 20) & 3u), hs = (int)(rw & 0xffffu);
         const unsigned e = s_we[rl * PW + pw];
         const int nw = (int)(e >> 8);
         int cls;
-        if (r.nh <= 0 || nw == 0) cls = CLS_EMPTY;
-        else if (r.slow) cls = CLS_SLOW;
-        else cls = (min(r.nh, N_DIM) - 1) * N_DIM - 1 + min(nw, N_DIM);
-        key = r.band * N_CLS + cls;
+        if (nh8 == 0 || nw == 0) cls = CLS_EMPTY;
+        else if (rw >> 22) cls = CLS_SLOW;
+        else cls = (nh8 - 1) * N_DIM - 1 + min(nw, N_DIM);
+        key = band * N_CLS + cls;
         const unsigned cell =
-            cls < CLS_EMPTY ? (unsigned)((r.hs - r.band * a.bg.step) * W + (int)(e & 255u)) : 0u;
+            cls < CLS_EMPTY ? (unsigned)((hs - band * a.bg.step) * W + (int)(e & 255u)) : 0u;
         recx = (unsigned)(s_nb[rl] + rem);
         recy = cell | ((unsigned)cls << 12);
       }
-      const unsigned peers = __match_any_sync(0xffffffffu, key);
-      const int leader = __ffs((int)peers) - 1;
+      // runs of adjacent lanes with the same key (match.any costs several hundred cycles here)
+      const int ln = tid & 31;
+      const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+      const unsigned heads = __ballot_sync(0xffffffffu, ln == 0 || key != prev);
+      const unsigned upto = (2u << ln) - 1u;          // lanes 0..ln (ln = 31: all)
+      const int my_head = 31 - __clz((int)(heads & upto));
+      const unsigned above = heads & ~upto;
+      const int run_end = above ? __ffs((int)above) - 1 : 32;
       int base = 0;
-      if (act && (tid & 31) == leader) base = atomicAdd(&(&s_cur[0][0])[key], __popc(peers));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (act) recs[base + __popc(peers & ((1u << (tid & 31)) - 1u))] = make_uint2(recx, recy);
+      if (act && ln == my_head) base = atomicAdd(&(&s_cur[0][0])[key], run_end - ln);
+      base = __shfl_sync(0xffffffffu, base, my_head);
+      if (act) recs[base + (ln - my_head)] = make_uint2(recx, recy);
     }
   }
   if (tid < NB_MAX * N_CLS) {
@@ -505,7 +537,7 @@ struct PoolArgs {
   int B, H, W, C, PH, PW;
   float spatial_scale;
   int bin_mode;
-  int nchunks, sg, n_slices;
+  int nchunks, sg, n_slices, nsub;
   int rec_cap;          // records resident at a time (multiple of 8)
   BandGeom bg;
   FastDiv divPW, divPHPW;
@@ -608,9 +640,12 @@ roi_pool_fwd_bins_kernel(const __grid_constant__ CUtensorMap tmap, const PoolArg
   // resident, barriers initialised and bands staged while the pre-pass still runs).
   stage(slice_begin);
   griddep_wait();
-  const int4 tb = a.table[img * NB_MAX + band];
-  const int g_begin = (int)((long long)tb.y * chunk / a.nchunks);
-  const int g_count = (int)((long long)tb.y * (chunk + 1) / a.nchunks) - g_begin;
+  // chunk = (sub-list, range of its groups): nchunks = nsub * ranges per sub-list
+  const int per_sub = a.nchunks / a.nsub;
+  const int sub = chunk / per_sub, part = chunk - sub * per_sub;
+  const int4 tb = a.table[(img * NB_MAX + band) * S_MAX + sub];
+  const int g_begin = (int)((long long)tb.y * part / per_sub);
+  const int g_count = (int)((long long)tb.y * (part + 1) / per_sub) - g_begin;
   if (g_count <= 0) {
     stage_wait();                                   // (no exit with a copy into this CTA in flight)
     return;
@@ -802,24 +837,28 @@ EncodeTiledFn tensor_map_encoder() {
 
 size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-int sort_rch(int PW) { return 24576 / PW < 1024 ? 24576 / PW : 1024; }
+int sort_rch(int PH, int PW) {
+  const int m = PH > PW ? PH : PW;
+  return 24576 / m < 1024 ? 24576 / m : 1024;
+}
 
-// s_wf u64[rch] | s_sh, s_bh, s_nb [rch] | s_we u16[rch*PW rounded to 8] | s_list u16[R]
-size_t sort_smem(int rch, int PW, int R, bool scan) {
+// s_wf u64[rch] | s_sh, s_bh, s_nb [rch] | s_we u16[rch*PW rounded to 8] | s_row u32[rch*PH] | s_list u16[R]
+size_t sort_smem(int rch, int PH, int PW, int R, bool scan) {
   return (size_t)rch * 8 + (size_t)rch * 12 + ((((size_t)rch * PW + 7) & ~(size_t)7) * 2) +
+         (size_t)rch * PH * 4 +
          (scan ? align16((size_t)R * 2) : 0) + 16;
 }
 
-// workspace: [bucket lists (R > 4096)] | table int4[(B+1)*NB_MAX] | recs uint2[cap]
+// workspace: [bucket lists (R > 4096)] | table int4[(B+1)*NB_MAX*S_MAX] | recs uint2[cap]
 struct BinsWs {
   size_t off_table, off_recs, total, cap;
 };
 BinsWs bins_ws(int B, int R, int PH, int PW) {
   BinsWs w;
   const size_t bucket = R > N_SCAN_MAX_R ? align16(bucket_workspace_bytes(B, R)) : 0;
-  w.cap = (((size_t)R * PH * PW + 7) & ~(size_t)7) + (size_t)(B + 1) * PAD_PER_IMAGE;
+  w.cap = (((size_t)R * PH * PW + 7) & ~(size_t)7) + (size_t)(B + 1) * S_MAX * PAD_PER_IMAGE;
   w.off_table = bucket;
-  w.off_recs = w.off_table + align16(sizeof(int4) * (size_t)(B + 1) * NB_MAX);
+  w.off_recs = w.off_table + align16(sizeof(int4) * (size_t)(B + 1) * NB_MAX * S_MAX);
   w.total = w.off_recs + w.cap * sizeof(uint2) + 16;
   return w;
 }
@@ -864,8 +903,8 @@ BinsPlan wssdl_roi::plan_bins(int B, int H, int W, int C, int R, int PH, int PW,
   if (cap < 8 * 64) return p;
   p.rec_cap = (int)cap;
   p.smem = 128 + row_bytes * p.g.Hb + cap * 8;
-  p.sort_rch = sort_rch(PW);
-  p.sort_smem = sort_smem(p.sort_rch, PW, R, p.scan);
+  p.sort_rch = sort_rch(PH, PW);
+  p.sort_smem = sort_smem(p.sort_rch, PH, PW, R, p.scan);
   if (p.sort_smem > (size_t)T_DYN_SMEM_MAX - 4096) return p;   // (+ the kernel's static arrays)
 
   // Ranges per band from a makespan model (us): a CTA stages the band (~2.5) and streams its
@@ -919,6 +958,16 @@ cudaError_t wssdl_roi::launch_fwd_bins(const BinsPlan& p, const float* bottom, c
   sa.bin_mode = bin_mode;
   sa.rch = p.sort_rch;
   sa.stride = grouped_stride > 0 ? grouped_stride : 0;
+  // sort CTAs per image: the pre-pass is issue bound on one SM per image, so while the batch
+  // leaves SMs idle every image is sorted by 2 or 4 CTAs into as many lists (a pooling CTA's
+  // range never spans two lists: nchunks is a multiple).  Not with in-kernel RoI lists (their
+  // order differs from CTA to CTA).
+  int nsub = 1;
+  if (sa.stride > 0 || perm != nullptr) {
+    for (int c = S_MAX; c > 1; c >>= 1)
+      if (p.nchunks % c == 0 && (long long)(B + 1) * c <= WSSDL_NUM_SMS) { nsub = c; break; }
+  }
+  sa.nsub = nsub;
   sa.bg = p.g;
   sa.divPH = make_fastdiv((unsigned)PH);
   sa.divStep = make_fastdiv((unsigned)p.g.step);
@@ -931,7 +980,7 @@ cudaError_t wssdl_roi::launch_fwd_bins(const BinsPlan& p, const float* bottom, c
   }
   {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(B + 1));
+    cfg.gridDim = dim3((unsigned)((B + 1) * nsub));
     cfg.blockDim = dim3(S_THREADS);
     cfg.dynamicSmemBytes = p.sort_smem;
     cfg.stream = s;
@@ -965,6 +1014,7 @@ cudaError_t wssdl_roi::launch_fwd_bins(const BinsPlan& p, const float* bottom, c
   a.spatial_scale = spatial_scale;
   a.bin_mode = bin_mode;
   a.nchunks = p.nchunks; a.sg = p.sg;
+  a.nsub = nsub;
   a.n_slices = C / N_SLICE;
   a.rec_cap = p.rec_cap;
   a.bg = p.g;
