@@ -58,5 +58,29 @@ meta = np.tile(np.array([[437, 583, 600.0 / 437]], np.float32), (B, 1))
 ops.detect_postprocess(r2, sc, dl, meta, roi_stride=S)
 ops.detect_postprocess(r2, sc, dl, meta, roi_stride=S, cls_agnostic=True, max_per_image=40)
 ops.bbox_transform_inv(b[:, :4].astype(np.float32), np.zeros((3000, 12), np.float32))
+# fused hot-path entry (PDL chain, grouped bin sort with sub-lists, -1 padding rows) and the
+# grouped RoI-pool entry, one and several images
+from wssdl_bus_b200.pipeline import HotPath  # noqa: E402
+from wssdl_bus_b200.rpn_msr import anchor_target_layer_tf_bus as atl  # noqa: E402
+from wssdl_bus_b200.rpn_msr import proposal_target_layer_tf_bus as ptl  # noqa: E402
+for nb in (1, 5):
+    f512 = torch.from_numpy(syn.feature_map(11, nb, H, W, 64)).cuda()
+    c_, r_, i_ = [torch.from_numpy(v).cuda() for v in syn.rpn_outputs(12, nb, H, W, 9)]
+    hot = HotPath(pre_nms_topN=200)
+    for kern in ("auto", "sorted"):
+        _lib.set_tuning("roi_fwd_kernel", kern)
+        out = hot.run(f512, c_, r_, i_)
+        ops.roi_pool_forward_grouped(f512, out["rois"], 300, 7, 7, 1 / 16.)
+_lib.set_tuning("roi_fwd_kernel", "auto")
+# device-resident target layers, both samplers
+np.random.seed(1)
+score = np.zeros((B, H, W, 18), np.float32)
+info4 = np.tile(np.array([[600, 800, 1.0]], np.float32), (B, 1))
+for sampler in ("host", "philox"):
+    atl.anchor_target_layer(score, gt, num, info4, None, [16, ], [8, 16, 32], "SNUBH", sampler=sampler, seed=3)
+    atl.anchor_target_layer(score, gt, num, info4, None, [16, ], [8, 16, 32], "VOC", sampler=sampler, seed=3)
+    pr = np.concatenate([np.hstack((np.full((260, 1), i, np.float32), syn.rois_for_pool(20 + i, 260)[:, 1:]))
+                         for i in range(B)])
+    ptl.proposal_target_layer(pr, gt, num, 3, True, False, sampler=sampler, seed=4)
 torch.cuda.synchronize()
 print("sanitize targets done")
