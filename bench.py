@@ -266,16 +266,33 @@ def run_ours(args):
             reg = (reg * 0.1).astype(np.float32)      # sigma 0.05: boxes hug their anchors
         d = [torch.from_numpy(x).to(dev) for x in (feat, cls, reg, info)]
         blob = DetectionBlob(n_img, post, device=dev)
-        ready = torch.cuda.Event()
-        ready.record()                                # (creates the handle the C ABI records into)
         side = torch.cuda.Stream(device=dev) if world > 1 else None
 
-        def step():
+        def tev():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()                                # (creates the handle the C ABI records into)
+            return e
+
+        warm_ready = tev()
+        # per timed step: start, the boundary between the two stages (recorded INSIDE the fused
+        # call by the C ABI, on the launching stream), end
+        # (at most five steps carry them: three event records per step cost ~2 % of a 0.46 ms step)
+        stride = max(1, (steps + 4) // 5)             # at most five marked steps
+        marked = [k for k in range(steps) if k % stride == 0]
+        marks = {k: (tev(), tev(), tev()) for k in marked}
+
+        def step(k=None):
             # ONE call of the fused entry (wssdl_hot_path_fwd): proposals -> RoI-pool forward.  The
             # detections (boxes, scores, counts: one blob) are complete after the proposals stage;
             # the entry records `ready` there and their all-gather runs on the communicator's
             # stream while the RoI pooling runs here.
-            p = hot.run(d[0], d[1], d[2], d[3], blob=blob, rois_ready=ready if world > 1 else None)
+            m = marks.get(k)
+            ready = m[1] if m else (warm_ready if world > 1 else None)
+            if m:
+                m[0].record()
+            p = hot.run(d[0], d[1], d[2], d[3], blob=blob, rois_ready=ready)
+            if m:
+                m[2].record()
             if world > 1:
                 side.wait_event(ready)
                 with torch.cuda.stream(side):
@@ -291,27 +308,14 @@ def run_ours(args):
         t0, t1 = ev(), ev()
         t0.record()
         for k in range(steps):
-            step()
+            step(k)
         t1.record()
         barrier()
         ms_total = t0.elapsed_time(t1)
-        # the two stages of the step timed separately (outside the timed region above): the two
-        # public ops back to back on the same inputs; the RoI pooling through the grouped entry
-        # the fused call uses
-        n_split = max(3, min(steps, 10))
-        roi_ev = [(ev(), ev()) for _ in range(n_split)]
-        prop_ev = [(ev(), ev()) for _ in range(n_split)]
-        for k in range(n_split):
-            prop_ev[k][0].record()
-            p = ops.proposals(d[1], d[2], d[3], hot.base, hot.feat_stride, hot.pre, hot.post,
-                              hot.thresh, hot.min_size, out=blob.views())
-            prop_ev[k][1].record()
-            roi_ev[k][0].record()
-            ops.roi_pool_forward_grouped(d[0], p["rois"], hot.post, hot.pooled_h, hot.pooled_w, hot.scale)
-            roi_ev[k][1].record()
-        torch.cuda.synchronize()
-        return (ms_total, float(np.mean([a.elapsed_time(b) for a, b in roi_ev])),
-                float(np.mean([a.elapsed_time(b) for a, b in prop_ev])), counts, d)
+        # the two stages of the marked steps, from the events recorded inside the timed region
+        prop_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks.values()]))
+        roi_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in marks.values()]))
+        return ms_total, roi_ms, prop_ms, counts, d
 
     # image i of the global batch has seed 7 * i (whatever the number of ranks); pad slots repeat
     seeds = [7 * int(i) for i in mine] + [7 * int(mine[-1] if len(mine) else 0)] * (B - len(mine))
@@ -394,13 +398,14 @@ def run_ours(args):
                          "images_per_launch": B,
                          "ms_per_launch": r["roi_ms"],
                          "note": "ms_per_launch covers the whole RoI-pool stage of one rank (bin sort "
-                                 "pre-pass and pooling kernel, wssdl_roi_pool_fwd_grouped), timed "
-                                 "with CUDA events around the stage run on its own right after "
-                                 "the timed steps"},
+                                 "pre-pass + pooling kernel) in the timed steps that carry events "
+                                 "(at most five, evenly spaced): from the event "
+                                 "wssdl_hot_path_fwd records on the launching stream between its "
+                                 "two stages to an event behind the call"},
             "kernels_ms_per_step": {"proposals_kernel": r["prop_ms"], "roi_pool_fwd": r["roi_ms"],
                                     "proposals_heavy": r["heavy_ms"]},
-            "kernels_note": "the two stages of the fused step timed one by one (outside the timed "
-                            "region); proposals_heavy: the same proposals call on regression deltas of sigma "
+            "kernels_note": "the two stages of the fused step, split by the event the call records "
+                            "between them (inside the timed region); proposals_heavy: the same proposals call on regression deltas of sigma "
                             "0.05 (boxes hug their anchors, the fused NMS visits thousands of "
                             "candidates before it has kept 300); not part of the timed step",
             # proposals_kernel + the RoI-pool kernels of one wssdl_hot_path_fwd call, per step
