@@ -106,11 +106,17 @@ size_t wssdl_roi_pool_fwd_workspace_bytes(int B, int R, int PH, int PW);
 
 /* Host-only query (no CUDA call): which forward kernel a call of this shape takes and its
  * launch geometry, for tests and tuning.  force: 0 = by shape, 1 = direct, 2 = tiled,
- * 3 = band, 4 = sorted bins.  out[8] = { kernel (0 direct, 1 tiled, 2 band, 3 sorted bins),
- * row bands per image, rows per band, first-row distance of two bands, RoI chunks per image,
- * RoIs whose bin edges are resident at a time, dynamic shared memory bytes, 1 if the RoI
- * lists are built in-kernel }; sorted bins also fills out[8] = 32-channel slices per CTA and
- * out[9] = bin records resident at a time.  `out` holds 10 ints.  Assumes aligned pointers. */
+ * 3 = band, 4 = sorted bins.  `out` holds 10 ints:
+ *   out[0] kernel (0 direct, 1 tiled, 2 band, 3 sorted bins)
+ *   out[1] row bands per image          out[2] rows per band
+ *   out[3] first-row distance of two bands
+ *   out[4] ranges per band (band / sorted: CTAs per band and slice) or RoI chunks per image (tiled)
+ *   out[5] RoIs whose bin edges are resident at a time (sorted bins: in the sort pre-pass)
+ *   out[6] dynamic shared memory bytes of the pooling kernel
+ *   out[7] 1 if the RoI lists are built in-kernel (no counting-sort launches)
+ *   out[8] sorted bins: 32-channel slices one CTA pools one after the other
+ *   out[9] sorted bins: threads per pooling CTA
+ * Assumes aligned pointers. */
 int wssdl_roi_pool_fwd_plan(int B, int H, int W, int C, int R, int PH, int PW,
                             int with_workspace, int force, int* out);
 
@@ -207,9 +213,9 @@ int wssdl_bbox_transform(const float* ex_rois, const float* gt_rois, int N, floa
  * the fly (generate_anchors.py:37-97 + shifts :55-71), bbox_transform_inv, clip_boxes,
  * _filter_boxes (:151-156), score sort + pre-NMS top-N (:129-133), NMS (:138), post-NMS
  * top-N (:139-146), batched over images: one CTA per image, everything in shared memory
- * (small batches: a thread-block cluster of 8 CTAs per image splits the keep-list NMS and
- * exchanges its partial bitmaps through distributed shared memory; same results;
- * WSSDL_PROPOSALS_CLUSTER=0|1 overrides the choice).
+ * (batches that leave SMs idle: a thread-block cluster of 2 / 4 / 8 CTAs per image splits both
+ * stages of the keep-list NMS rounds and exchanges alive bits and column masks through
+ * distributed shared memory; same results; WSSDL_TUNE_PROPOSALS_CLUSTER overrides the choice).
  *
  * cls_prob  [B,H,W,2A] f32 NHWC (fg score of anchor a = channel A+a, :86)
  * bbox_pred [B,H,W,4A] f32 NHWC (deltas of anchor a = channels 4a..4a+3, :106)

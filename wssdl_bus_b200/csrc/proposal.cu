@@ -181,15 +181,15 @@ __device__ unsigned radix_select(KeyFn key_at, int n, int K, unsigned* s_hist /*
   return prefix;
 }
 
-// CS > 1: a thread-block cluster of CS CTAs works on ONE image (small batches leave most of the
-// machine idle, and the keep-list NMS of a training-shape image -- up to 2000 candidates against
-// up to 2000 kept boxes -- is issue bound on a single SM).  Every CTA of the cluster runs the
-// whole pipeline redundantly on identical state (decode, select and sort are deterministic),
-// except step A of the NMS rounds: CTA r tests the round's candidates against the kept boxes
-// k == r (mod CS) only, the partial "suppressed" bitmaps are exchanged through distributed
-// shared memory (each CTA stores its 256 bits into every peer's slot, one cluster barrier per
-// round, two slot sets so a CTA one round ahead cannot overwrite what a peer still reads), and
-// the rounds continue in lock step.  CTA 0 writes the outputs.
+// CS > 1: a thread-block cluster of CS CTAs (2, 4 or 8) works on ONE image (batches that leave
+// SMs idle: one image's pipeline is issue bound on a single SM).  Every CTA of the cluster runs
+// phases 1-3 redundantly on identical state (keys, select, sort and decode are deterministic);
+// the NMS rounds are split: CTA r owns 256 / CS candidates of the round, 4 * CS threads each, for
+// BOTH stage A (candidate against the kept list) and stage B (the candidate's column over the
+// earlier candidates of the chunk).  Alive words and columns are exchanged through distributed
+// shared memory -- every CTA stores its part into every CTA's copy, ONE cluster barrier per
+// round, two slot sets so that a CTA one round ahead cannot overwrite what a peer still reads --
+// and stages C and D run redundantly, so the kept lists stay identical.  CTA 0 writes the outputs.
 constexpr int XCHG_WORDS = CHUNK / 32;
 
 template <int CS>
