@@ -228,8 +228,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from wssdl_bus_b200 import ops
-    from wssdl_bus_b200.pipeline import (DetectionBlob, HostPipeline, HotPath, bind_to_gpu_numa_node,
-                                         shard_images)
+    from wssdl_bus_b200.pipeline import (DetectionBlob, HostPipeline, HotPath, PipelinedHotPath,
+                                         bind_to_gpu_numa_node, shard_images)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -254,9 +254,12 @@ def run_ours(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def device_leg(n_img, seeds, steps, heavy=False):
+    def device_leg(n_img, seeds, steps, heavy=False, pipelined=False):
         """K steps of proposals -> (async all-gather of the detection blob) -> RoI-pool forward on
-        n_img images resident in HBM.  Returns (ms_total, roi_ms, prop_ms, counts)."""
+        n_img images resident in HBM.  Returns (ms_total, roi_ms, prop_ms, counts).
+        pipelined: consecutive steps overlap (pipeline.PipelinedHotPath: step k+1's proposals run
+        on a high-priority stream while step k is pooled); else one fused call per step, steps
+        strictly one after the other."""
         feat = np.concatenate([syn.feature_map(s_, 1, CFG["H"], CFG["W"], CFG["C"]) for s_ in seeds])
         parts = [syn.rpn_outputs(s_ + 1, 1, CFG["H"], CFG["W"], CFG["A"]) for s_ in seeds]
         cls = np.concatenate([p_[0] for p_ in parts])
@@ -300,8 +303,17 @@ def run_ours(args):
                 work.wait()                           # the step ends when the gather has landed
             return p
 
+        if pipelined:
+            php = PipelinedHotPath(hot, n_img, device=dev, gather=world > 1)
+            marks = {k: (tev(), tev(), tev(), tev()) for k in marked}
+
+            def step(k=None):                         # noqa: F811
+                return php.submit(d[0], d[1], d[2], d[3], marks=marks.get(k))
+
         for _ in range(Wm):
             p = step()
+        if pipelined:
+            php.drain()
         counts = p["counts"].cpu().numpy()
         del p
         barrier()
@@ -309,12 +321,18 @@ def run_ours(args):
         t0.record()
         for k in range(steps):
             step(k)
+        if pipelined:
+            php.drain()                               # the timed region ends when every step has
         t1.record()
         barrier()
         ms_total = t0.elapsed_time(t1)
         # the two stages of the marked steps, from the events recorded inside the timed region
-        prop_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks.values()]))
-        roi_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in marks.values()]))
+        if pipelined:
+            prop_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks.values()]))
+            roi_ms = float(np.mean([m[2].elapsed_time(m[3]) for m in marks.values()]))
+        else:
+            prop_ms = float(np.mean([m[0].elapsed_time(m[1]) for m in marks.values()]))
+            roi_ms = float(np.mean([m[1].elapsed_time(m[2]) for m in marks.values()]))
         return ms_total, roi_ms, prop_ms, counts, d
 
     # image i of the global batch has seed 7 * i (whatever the number of ranks); pad slots repeat
@@ -322,8 +340,15 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_total, roi_ms, prop_ms, counts, d = device_leg(B, seeds, K)
+    pipelined = args.pipelined == 1 or (args.pipelined < 0 and B <= 64)
+    ms_total, roi_ms, prop_ms, counts, d = device_leg(B, seeds, K, pipelined=pipelined)
     clocks = sampler.summary() if sampler else None
+    # the latency of ONE step (fused call, nothing overlapped) next to the pipelined throughput
+    serial_ms = None
+    if pipelined:
+        lat = device_leg(B, seeds, max(3, min(K, 10)), pipelined=False)
+        serial_ms = lat[0] / max(3, min(K, 10))
+        del lat
     # proposals where the NMS has to work: boxes that hug their anchors suppress each other heavily
     heavy = device_leg(B, seeds, max(3, K // 2), heavy=True)
     heavy_ms = heavy[2]
@@ -371,8 +396,8 @@ def run_ours(args):
             del hp, gb
 
     # max over ranks
-    names = ["ms_total", "roi_ms", "prop_ms", "heavy_ms", "weak"] + sorted(e2e_ms)
-    vals = [ms_total, roi_ms, prop_ms, heavy_ms, weak or 0.0] + [e2e_ms[k] for k in sorted(e2e_ms)]
+    names = ["ms_total", "roi_ms", "prop_ms", "heavy_ms", "weak", "serial_ms"] + sorted(e2e_ms)
+    vals = [ms_total, roi_ms, prop_ms, heavy_ms, weak or 0.0, serial_ms or 0.0] + [e2e_ms[k] for k in sorted(e2e_ms)]
     t = torch.tensor(vals, device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -410,10 +435,17 @@ def run_ours(args):
                             "candidates before it has kept 300); not part of the timed step",
             # proposals_kernel + the RoI-pool kernels of one wssdl_hot_path_fwd call, per step
             "gpu_launches": (1 + roi_launches) * K,
+            "pipelined": bool(pipelined),
             "clocks": clocks,
             "rois_per_image": [int(counts.min()), int(counts.max())],
             "numa_node_rank0": numa,
         }
+        if pipelined:
+            line["pipelined_note"] = ("consecutive steps overlap: step k+1's proposals (one CTA per image, "
+                                      "high-priority stream) run while step k is pooled; RoI blobs double "
+                                      "buffered (pipeline.PipelinedHotPath).  serial_ms_per_step: the same "
+                                      "step as ONE fused call with nothing overlapped (its latency)")
+            line["serial_ms_per_step"] = r["serial_ms"]
         if weak:
             wms = r["weak"] / K
             line["weak_scaling"] = {"images_per_gpu": args.weak_images,
@@ -463,6 +495,11 @@ def main():
     ap.add_argument("--images", type=int, default=256, help="global batch, sharded over the ranks")
     ap.add_argument("--weak-images", type=int, default=256, help="images per GPU of the weak-scaling leg")
     ap.add_argument("--no-weak", action="store_true")
+    ap.add_argument("--pipelined", type=int, default=-1,
+                    help="1: consecutive steps overlap on two streams (PipelinedHotPath); 0: one fused "
+                         "call per step, steps one after the other; -1: pipelined when a rank's batch "
+                         "is at most 64 images (one image's proposals are latency bound and leave "
+                         "most SMs idle on small batches)")
     ap.add_argument("--e2e-chunk", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")

@@ -342,6 +342,16 @@ int wssdl_hot_path_fwd(const float* feat, const float* cls_prob, const float* bb
                        int* counts, float* top, int* argmax, void* workspace,
                        size_t workspace_bytes, wssdl_stream_t stream, void* rois_ready_event);
 
+/* Stage 1 of the hot path on its own (the proposals with the blob convention above: unused rows
+ * carry batch index -1; always one CTA per image, i.e. least SM time rather than least latency),
+ * for callers that pipeline the two stages over consecutive batches on two streams; stage 2 is
+ * wssdl_roi_pool_fwd_grouped on the blob. */
+int wssdl_hot_path_proposals(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                             int info_stride, int B, int H, int W, int A,
+                             const float* base_anchors, int feat_stride, int pre_nms_topN,
+                             int post_nms_topN, double nms_thresh, int nms_mode, float min_size,
+                             float* rois, float* scores, int* counts, wssdl_stream_t stream);
+
 /* wssdl_roi_pool_fwd for image-major RoIs: row r belongs to image r / roi_stride (R = B *
  * roi_stride); rows whose batch index is not their block's image pool to zeros / -1.  The layout
  * wssdl_proposals writes; saves the RoI grouping pre-pass of the sorted-bins kernel. */

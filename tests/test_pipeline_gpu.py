@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from wssdl_bus_b200 import ops, synthetic as syn
-from wssdl_bus_b200.pipeline import HostPipeline, HotPath
+from wssdl_bus_b200.pipeline import HostPipeline, HotPath, PipelinedHotPath
 
 pytestmark = pytest.mark.gpu
 
@@ -127,3 +127,28 @@ def test_fused_entry_equals_the_two_ops_back_to_back(B, kern, tuning):
     # without argmax
     g = hot.run(x, cls, reg, info, need_argmax=False)
     assert g["argmax"] is None and torch.equal(g["top"], f["top"])
+
+
+def test_pipelined_hot_path_equals_the_fused_call_batch_by_batch():
+    """PipelinedHotPath (proposals of batch k+1 on a high-priority stream while batch k is pooled,
+    double-buffered RoI blobs) over six different batches, more than the two blob slots: every
+    batch's outputs equal the fused call's on the same inputs, whatever overlapped."""
+    B = 6
+    hot = HotPath(pre_nms_topN=400)
+    batches = []
+    for k in range(6):
+        feat, cls, reg, info = _inputs(800 + 10 * k, B)
+        batches.append([torch.from_numpy(v).cuda() for v in (feat, cls, reg, info)])
+    want = [hot.run(*b) for b in batches]
+    torch.cuda.synchronize()
+    php = PipelinedHotPath(hot, B)
+    got = [php.submit(*b) for b in batches]
+    php.drain()
+    torch.cuda.synchronize()
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert g["done"].query()
+        # (slots are reused: RoIs / scores / counts of batch k live in blob k % 2 until batch k+2)
+        assert torch.equal(g["top"], w["top"]) and torch.equal(g["argmax"], w["argmax"]), k
+    for k in (4, 5):
+        for key in ("rois", "scores", "counts"):
+            assert torch.equal(got[k][key], want[k][key]), (k, key)

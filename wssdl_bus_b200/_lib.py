@@ -55,6 +55,8 @@ SIGNATURES = {
     "wssdl_hot_path_fwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "wssdl_hot_path_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _d, _i, _f,
                                 _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "wssdl_hot_path_proposals": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _d, _i, _f,
+                                      _vp, _vp, _vp, _vp]),
     "wssdl_roi_pool_fwd_grouped": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp,
                                         _sz, _vp]),
     "wssdl_roi_targets_workspace_bytes": (_sz, [_i, _i, _i]),

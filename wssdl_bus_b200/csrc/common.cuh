@@ -35,7 +35,8 @@ int wssdl_proposals_impl(const float* cls_prob, const float* bbox_pred, const fl
                          int info_stride, int B, int H, int W, int A, const float* base_anchors,
                          int feat_stride, int pre_nms_topN, int post_nms_topN, double nms_thresh,
                          int nms_mode, float min_size, float* rois, float* scores, int* anchor_idx,
-                         int* counts, float* decoded, wssdl_stream_t stream, float pad_batch_index);
+                         int* counts, float* decoded, wssdl_stream_t stream, float pad_batch_index,
+                         int one_cta_per_image);
 
 static inline cudaStream_t to_cuda(wssdl_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

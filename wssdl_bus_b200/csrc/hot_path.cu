@@ -25,11 +25,28 @@ extern "C" int wssdl_hot_path_fwd(const float* feat, const float* cls_prob, cons
   if (B < 0 || post_nms_topN <= 0 || (long long)B * post_nms_topN >= (1ll << 31)) return WSSDL_EINVAL;
   int rc = wssdl_proposals_impl(cls_prob, bbox_pred, im_info, info_stride, B, H, W, A, base_anchors,
                                 feat_stride, pre_nms_topN, post_nms_topN, nms_thresh, nms_mode,
-                                min_size, rois, scores, nullptr, counts, nullptr, stream, -1.0f);
+                                min_size, rois, scores, nullptr, counts, nullptr, stream, -1.0f, 0);
   if (rc != WSSDL_OK) return rc;
   if (rois_ready_event)   // rois / scores / counts are final here: a consumer on another stream
     WSSDL_RETURN_IF_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(rois_ready_event), to_cuda(stream)));
   return wssdl_roi_pool_fwd_impl(feat, rois, B, H, W, C, B * post_nms_topN, PH, PW, spatial_scale,
                                  bin_mode, top, argmax, workspace, workspace_bytes, stream,
                                  post_nms_topN);
+}
+
+// Stage 1 of the hot path on its own, for callers that pipeline the two stages over consecutive
+// batches on two streams (pipeline.PipelinedHotPath: the proposals of batch k+1 run while batch k
+// is pooled): wssdl_proposals with the hot path's blob convention (unused rows carry batch index
+// -1) and always one CTA per image: overlapped with another batch's pooling it should take the
+// least SM time, not the least latency.  Stage 2 is wssdl_roi_pool_fwd_grouped on the blob.
+extern "C" int wssdl_hot_path_proposals(const float* cls_prob, const float* bbox_pred,
+                                        const float* im_info, int info_stride, int B, int H, int W,
+                                        int A, const float* base_anchors, int feat_stride,
+                                        int pre_nms_topN, int post_nms_topN, double nms_thresh,
+                                        int nms_mode, float min_size, float* rois, float* scores,
+                                        int* counts, wssdl_stream_t stream) {
+  if (post_nms_topN <= 0) return WSSDL_EINVAL;
+  return wssdl_proposals_impl(cls_prob, bbox_pred, im_info, info_stride, B, H, W, A, base_anchors,
+                              feat_stride, pre_nms_topN, post_nms_topN, nms_thresh, nms_mode,
+                              min_size, rois, scores, nullptr, counts, nullptr, stream, -1.0f, 1);
 }

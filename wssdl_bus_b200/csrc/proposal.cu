@@ -637,14 +637,15 @@ extern "C" int wssdl_proposals(const float* cls_prob, const float* bbox_pred,
   (void)workspace; (void)workspace_bytes;
   return wssdl_proposals_impl(cls_prob, bbox_pred, im_info, info_stride, B, H, W, A, base_anchors,
                               feat_stride, pre_nms_topN, post_nms_topN, nms_thresh, nms_mode,
-                              min_size, rois, scores, anchor_idx, counts, decoded, stream, 0.f);
+                              min_size, rois, scores, anchor_idx, counts, decoded, stream, 0.f, 0);
 }
 
 int wssdl_proposals_impl(const float* cls_prob, const float* bbox_pred, const float* im_info,
                          int info_stride, int B, int H, int W, int A, const float* base_anchors,
                          int feat_stride, int pre_nms_topN, int post_nms_topN, double nms_thresh,
                          int nms_mode, float min_size, float* rois, float* scores, int* anchor_idx,
-                         int* counts, float* decoded, wssdl_stream_t stream, float pad_batch_index) {
+                         int* counts, float* decoded, wssdl_stream_t stream, float pad_batch_index,
+                         int one_cta_per_image) {
   if (B < 0 || H <= 0 || W <= 0 || A <= 0 || info_stride < 3) return WSSDL_EINVAL;
   if (nms_mode != WSSDL_NMS_GE_F64 && nms_mode != WSSDL_NMS_GT_F32) return WSSDL_EINVAL;
   if (B == 0) return WSSDL_OK;
@@ -692,7 +693,9 @@ int wssdl_proposals_impl(const float* cls_prob, const float* bbox_pred, const fl
     if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
     return n >= B;
   };
-  const int ctune = wssdl_tuning(WSSDL_TUNE_PROPOSALS_CLUSTER);
+  // (one_cta_per_image: the caller overlaps this launch with other kernels and wants the least
+  // SM time, not the least latency)
+  const int ctune = one_cta_per_image ? 0 : wssdl_tuning(WSSDL_TUNE_PROPOSALS_CLUSTER);
   int cs = 1;
   if (ctune == 2 || ctune == 4 || ctune == 8) {
     cs = ctune;

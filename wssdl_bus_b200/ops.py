@@ -355,7 +355,7 @@ def bbox_transform(ex_rois, gt_rois):
 # ------------------------------------------------------------------ proposals
 def proposals(cls_prob, bbox_pred, im_info, base_anchors, feat_stride, pre_nms_topN,
               post_nms_topN, nms_thresh, min_size, want_decoded=False, out=None,
-              nms_mode=NMS_GE_F64):
+              nms_mode=NMS_GE_F64, pad_rows_invalid=False):
     """Batched fused proposal layer.  cls_prob [B,H,W,2A], bbox_pred [B,H,W,4A] (NHWC),
     im_info [B,>=3].  Returns dict of device tensors: rois [B*post,5], scores [B*post],
     anchor_idx [B*post] i32, counts [B] i32 (+ decoded [B,H*W*A,4] when asked).
@@ -363,7 +363,9 @@ def proposals(cls_prob, bbox_pred, im_info, base_anchors, feat_stride, pre_nms_t
     contiguous detection blob, pipeline.DetectionBlob, so that one all-gather moves them).
     nms_mode: NMS_GE_F64 (cpu_nms, cfg.USE_GPU_NMS False) or NMS_GT_F32 (gpu_nms).
     pre_nms_topN <= 0 / post_nms_topN <= 0: no truncation (proposal_layer_tf_bus.py:130, :139);
-    the stride of the blob is then min(pre_nms_topN or H*W*A, H*W*A) (<= 4096 on the device)."""
+    the stride of the blob is then min(pre_nms_topN or H*W*A, H*W*A) (<= 4096 on the device).
+    pad_rows_invalid: the hot path's blob convention (wssdl_hot_path_proposals): the unused rows of
+    an image's block carry batch index -1 instead of 0 and pool to zeros / -1 (no anchor_idx)."""
     cls_prob = _cuda(cls_prob, torch.float32)
     dev = cls_prob.device
     bbox_pred = _cuda(bbox_pred, torch.float32, dev)
@@ -398,6 +400,16 @@ def proposals(cls_prob, bbox_pred, im_info, base_anchors, feat_stride, pre_nms_t
                    if want_decoded else None)
         ws = _workspace(_lib.lib().wssdl_proposals_workspace_bytes(B, H, W, A, int(pre_nms_topN),
                                                                    post), dev)
+        if pad_rows_invalid:
+            if want_decoded:
+                raise ValueError("pad_rows_invalid: no decoded boxes through the hot-path stage entry")
+            rc = _lib.lib().wssdl_hot_path_proposals(
+                _ptr(cls_prob), _ptr(bbox_pred), _ptr(im_info), im_info.shape[1], B, H, W, A,
+                base.ctypes.data_as(_vp), int(feat_stride), int(pre_nms_topN), post,
+                float(nms_thresh), int(nms_mode), float(min_size), _ptr(rois), _ptr(scores),
+                _ptr(counts), _stream(dev))
+            _lib.check(rc, "wssdl_hot_path_proposals")
+            return dict(rois=rois, scores=scores, counts=counts, post_nms_topN=post)
         rc = _lib.lib().wssdl_proposals(
             _ptr(cls_prob), _ptr(bbox_pred), _ptr(im_info), im_info.shape[1], B, H, W, A,
             base.ctypes.data_as(_vp), int(feat_stride), int(pre_nms_topN), post,

@@ -150,6 +150,84 @@ class DetectionBlob:
         return self._split(g, self.n_local, self.post, self.o_scores, self.o_counts), work
 
 
+class PipelinedHotPath:
+    """The hot path software-pipelined over CONSECUTIVE batches on two streams.
+
+    One image's proposals are a latency-bound kernel (one CTA, or one cluster, per image) that
+    leaves most of the GPU idle when the batch is small, and the RoI pooling of a batch cannot
+    start before its proposals are done.  Consecutive batches are independent, so batch k+1's
+    proposals run on a high-priority stream WHILE batch k is pooled on the other stream: their
+    CTAs take SMs as pooling CTAs retire, and the pooling kernel never waits for them.  The RoI
+    blobs are double buffered (`depth` slots): batch k+depth's proposals wait for batch k's pooling
+    (and for its all-gather) before they overwrite slot k % depth.
+
+    submit() enqueues one batch and returns its outputs (device tensors; complete once `done`
+    has fired, or after drain()).  Inputs must be ready on the submitting stream and stay
+    untouched until the batch is done.  world_size > 1: the packed detections of every batch are
+    all-gathered behind its proposals (one collective, on the communicator's stream)."""
+
+    def __init__(self, hot, n_images, device=None, depth=2, gather=False, group=None):
+        self.hot, self.n, self.depth = hot, int(n_images), int(depth)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.s_prop = torch.cuda.Stream(device=self.dev, priority=-1)
+        self.s_pool = torch.cuda.Stream(device=self.dev)
+        self.blobs = [DetectionBlob(self.n, hot.post, device=self.dev) for _ in range(self.depth)]
+        self.pool_done = [None] * self.depth
+        self.gather_work = [None] * self.depth
+        self.gather, self.group = bool(gather), group
+        self.k = 0
+
+    def submit(self, feat, cls_prob, bbox_pred, im_info, need_argmax=True, marks=None):
+        """marks: optional (e0, e1, e2, e3) timing events recorded around the proposals (on the
+        proposals stream) and around the RoI-pool stage (on the pooling stream)."""
+        hot, b = self.hot, self.k % self.depth
+        blob = self.blobs[b]
+        cur = torch.cuda.current_stream(self.dev)
+        self.s_prop.wait_stream(cur)                       # inputs are ready
+        with torch.cuda.stream(self.s_prop):
+            if self.pool_done[b] is not None:
+                self.s_prop.wait_event(self.pool_done[b])  # slot b's RoIs have been pooled
+            if self.gather_work[b] is not None:
+                self.gather_work[b].wait()                 # ... and gathered
+                self.gather_work[b] = None
+            if marks:
+                marks[0].record()
+            p = ops.proposals(cls_prob, bbox_pred, im_info, hot.base, hot.feat_stride, hot.pre,
+                              hot.post, hot.thresh, hot.min_size, out=blob.views(),
+                              pad_rows_invalid=True)
+            if marks:
+                marks[1].record()
+            ready = torch.cuda.Event()
+            ready.record()
+            if self.gather:
+                p["gathered"], self.gather_work[b] = blob.all_gather(self.group, async_op=True)
+        with torch.cuda.stream(self.s_pool):
+            self.s_pool.wait_event(ready)
+            if marks:
+                marks[2].record()
+            top, argmax = ops.roi_pool_forward_grouped(feat, p["rois"], hot.post, hot.pooled_h,
+                                                       hot.pooled_w, hot.scale, hot.bin_mode,
+                                                       need_argmax)
+            if marks:
+                marks[3].record()
+            done = torch.cuda.Event()
+            done.record()
+        self.pool_done[b] = done
+        p["top"], p["argmax"], p["done"] = top, argmax, done
+        self.k += 1
+        return p
+
+    def drain(self):
+        """The submitting stream waits for everything submitted so far (incl. the gathers)."""
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_stream(self.s_pool)
+        for b, w in enumerate(self.gather_work):
+            if w is not None:
+                w.wait()
+                self.gather_work[b] = None
+        cur.wait_stream(self.s_prop)
+
+
 def all_gather_blobs(tensors, group=None, async_op=False):
     """all_gather_into_tensor of several [n_local, ...] tensors (NCCL over NVLink on GPUs,
     gloo in the CPU tests): -> list of [world, n_local, ...].
