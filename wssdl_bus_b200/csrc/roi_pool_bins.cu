@@ -197,6 +197,9 @@ __device__ __forceinline__ void pool_row(Acc& a, unsigned q, unsigned qx, int k0
   if (W0 <= 1 && NW >= 2) { const float4 v0 = lds128<128>(q), v1 = lds128<128>(qx); upd8<HAS_ARGMAX>(a, v0, v1, k0 + KS, x); }
   if (W0 <= 2 && NW >= 3) { const float4 v0 = lds128<256>(q), v1 = lds128<256>(qx); upd8<HAS_ARGMAX>(a, v0, v1, k0 + 2 * KS, x); }
   if (W0 <= 3 && NW >= 4) { const float4 v0 = lds128<384>(q), v1 = lds128<384>(qx); upd8<HAS_ARGMAX>(a, v0, v1, k0 + 3 * KS, x); }
+  if (W0 <= 4 && NW >= 5) { const float4 v0 = lds128<512>(q), v1 = lds128<512>(qx); upd8<HAS_ARGMAX>(a, v0, v1, k0 + 4 * KS, x); }
+  if (W0 <= 5 && NW >= 6) { const float4 v0 = lds128<640>(q), v1 = lds128<640>(qx); upd8<HAS_ARGMAX>(a, v0, v1, k0 + 5 * KS, x); }
+  if (W0 <= 6 && NW >= 7) { const float4 v0 = lds128<768>(q), v1 = lds128<768>(qx); upd8<HAS_ARGMAX>(a, v0, v1, k0 + 6 * KS, x); }
 #else
   if (W0 <= 0 && NW >= 1) {
     const float4 a0 = lds128<0>(q), b0 = lds128<0>(qx);
@@ -220,6 +223,20 @@ __device__ __forceinline__ void pool_row(Acc& a, unsigned q, unsigned qx, int k0
     } else {
       upd8<HAS_ARGMAX>(a, a2, b2, k0 + 2 * KS, x);
     }
+  }
+  if (NW >= 5) {
+    const float4 a4 = lds128<512>(q), b4 = lds128<512>(qx);
+    if (NW >= 6) {
+      const float4 a5 = lds128<640>(q), b5 = lds128<640>(qx);
+      upd8<HAS_ARGMAX>(a, a4, b4, k0 + 4 * KS, x);
+      upd8<HAS_ARGMAX>(a, a5, b5, k0 + 5 * KS, x);
+    } else {
+      upd8<HAS_ARGMAX>(a, a4, b4, k0 + 4 * KS, x);
+    }
+  }
+  if (NW >= 7) {
+    const float4 a6 = lds128<768>(q), b6 = lds128<768>(qx);
+    upd8<HAS_ARGMAX>(a, a6, b6, k0 + 6 * KS, x);
   }
 #endif
 }
@@ -781,6 +798,9 @@ roi_pool_fwd_bins_kernel(const __grid_constant__ CUtensorMap tmap, const PoolArg
           case 2: pool_rows<2, HAS_ARGMAX, LINEAR>(acc, q, key, nhc, row_bytes, W, x); break;
           case 3: pool_rows<3, HAS_ARGMAX, LINEAR>(acc, q, key, nhc, row_bytes, W, x); break;
           case 4: pool_rows<4, HAS_ARGMAX, LINEAR>(acc, q, key, nhc, row_bytes, W, x); break;
+          case 5: pool_rows<5, HAS_ARGMAX, LINEAR>(acc, q, key, nhc, row_bytes, W, x); break;
+          case 6: pool_rows<6, HAS_ARGMAX, LINEAR>(acc, q, key, nhc, row_bytes, W, x); break;
+          case 7: pool_rows<7, HAS_ARGMAX, LINEAR>(acc, q, key, nhc, row_bytes, W, x); break;
           default: pool_rows_any<HAS_ARGMAX, LINEAR>(acc, q, key, nhc, nwc, row_bytes, W, x); break;
         }
         if ((rec.y & RECY_PAD) == 0) {
