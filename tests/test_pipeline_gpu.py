@@ -152,3 +152,20 @@ def test_pipelined_hot_path_equals_the_fused_call_batch_by_batch():
     for k in (4, 5):
         for key in ("rois", "scores", "counts"):
             assert torch.equal(got[k][key], want[k][key]), (k, key)
+
+
+@pytest.mark.parametrize("C", [48, 16, 100])
+def test_fused_entry_with_channel_counts_the_band_kernels_do_not_take(C):
+    """C % 32 != 0 (tiled / direct forward kernels behind the fused entry): the -1 padding rows
+    still pool to zeros / -1 and the kept rows equal the two ops back to back."""
+    B = 3
+    c = syn.C1
+    feat = syn.feature_map(900 + C, B, c["H"], c["W"], C)
+    cls, reg, info = syn.rpn_outputs(901 + C, B, c["H"], c["W"], c["A"])
+    x = torch.from_numpy(feat).cuda()
+    hot = HotPath(pre_nms_topN=150)
+    f = hot.run(x, cls, reg, info)
+    u = hot.run(x, cls, reg, info, fused=False)
+    valid = (torch.arange(300, device="cuda")[None, :] < f["counts"][:, None]).reshape(-1)
+    assert torch.equal(f["top"][valid], u["top"][valid]) and torch.equal(f["argmax"][valid], u["argmax"][valid])
+    assert not bool(f["top"][~valid].any()) and bool(torch.all(f["argmax"][~valid] == -1))
