@@ -1,5 +1,6 @@
 #!/bin/bash
-# Scaling run on one 8-GPU box: bench.py at the given N values (weak scaling, 256 images per GPU).
+# Scaling run on one 8-GPU box: bench.py at the given N values (strong scaling of the 256-image
+# batch; the weak-scaling value is a key of the same line).
 set +e
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/scale_gpus.csv 2>&1
