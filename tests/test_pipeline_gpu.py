@@ -129,9 +129,10 @@ def test_fused_entry_equals_the_two_ops_back_to_back(B, kern, tuning):
     assert g["argmax"] is None and torch.equal(g["top"], f["top"])
 
 
-def test_pipelined_hot_path_equals_the_fused_call_batch_by_batch():
+@pytest.mark.parametrize("depth,need_argmax", [(2, True), (3, False)])
+def test_pipelined_hot_path_equals_the_fused_call_batch_by_batch(depth, need_argmax):
     """PipelinedHotPath (proposals of batch k+1 on a high-priority stream while batch k is pooled,
-    double-buffered RoI blobs) over six different batches, more than the two blob slots: every
+    `depth` RoI blob slots) over six different batches, more than the blob slots: every
     batch's outputs equal the fused call's on the same inputs, whatever overlapped."""
     B = 6
     hot = HotPath(pre_nms_topN=400)
@@ -141,14 +142,15 @@ def test_pipelined_hot_path_equals_the_fused_call_batch_by_batch():
         batches.append([torch.from_numpy(v).cuda() for v in (feat, cls, reg, info)])
     want = [hot.run(*b) for b in batches]
     torch.cuda.synchronize()
-    php = PipelinedHotPath(hot, B)
-    got = [php.submit(*b) for b in batches]
+    php = PipelinedHotPath(hot, B, depth=depth)
+    got = [php.submit(*b, need_argmax=need_argmax) for b in batches]
     php.drain()
     torch.cuda.synchronize()
     for k, (g, w) in enumerate(zip(got, want)):
         assert g["done"].query()
-        # (slots are reused: RoIs / scores / counts of batch k live in blob k % 2 until batch k+2)
-        assert torch.equal(g["top"], w["top"]) and torch.equal(g["argmax"], w["argmax"]), k
+        # (slots are reused: RoIs / scores / counts of batch k live in blob k % depth until batch k+depth)
+        assert torch.equal(g["top"], w["top"]), k
+        assert (g["argmax"] is None) if not need_argmax else torch.equal(g["argmax"], w["argmax"]), k
     for k in (4, 5):
         for key in ("rois", "scores", "counts"):
             assert torch.equal(got[k][key], want[k][key]), (k, key)
