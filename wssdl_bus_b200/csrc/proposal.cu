@@ -182,8 +182,9 @@ __device__ unsigned radix_select(KeyFn key_at, int n, int K, unsigned* s_hist /*
 }
 
 // CS > 1: a thread-block cluster of CS CTAs (2, 4 or 8) works on ONE image (batches that leave
-// SMs idle: one image's pipeline is issue bound on a single SM).  Every CTA of the cluster runs
-// phases 1-3 redundantly on identical state (keys, select, sort and decode are deterministic);
+// SMs idle: one image's pipeline is issue bound on a single SM).  The score keys are loaded once
+// per cluster (all-gather through distributed shared memory); every CTA then runs phases 2-3
+// redundantly on identical state (select, sort and decode are deterministic);
 // the NMS rounds are split: CTA r owns 256 / CS candidates of the round, 4 * CS threads each, for
 // BOTH stage A (candidate against the kept list) and stage B (the candidate's column over the
 // earlier candidates of the chunk).  Alive words and columns are exchanged through distributed
@@ -244,27 +245,43 @@ proposals_kernel(const PropParams p) {
   if (tid == 0) s_cnt[1] = 0;
   // (eight independent loads in flight per thread: one at a time the 17 strided loads of a thread
   // were 12 % of the kernel, all of it load latency)
+  // Cluster: CTA r loads the scores of its 1/CS share of the anchors only and stores the keys into
+  // every CTA's copy (distributed shared memory all-gather, published by one cluster barrier).
   {
     const float* sc_img = p.cls_prob + (size_t)img * p.H * p.W * (2 * p.A) + p.A;
-    for (int a0 = 0; a0 < p.NA; a0 += 8 * PT) {
+    const int a_lo = CS > 1 ? (int)((long long)p.NA * crank / CS) : 0;
+    const int a_hi = CS > 1 ? (int)((long long)p.NA * (crank + 1) / CS) : p.NA;
+    unsigned* peer_keys[CS];
+    if constexpr (CS > 1) {
+#pragma unroll
+      for (int r = 0; r < CS; ++r) peer_keys[r] = cg::this_cluster().map_shared_rank(s_keys, r);
+    } else {
+      peer_keys[0] = s_keys;
+    }
+    for (int a0 = a_lo; a0 < a_hi; a0 += 8 * PT) {
       float sc[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int a = a0 + q * PT + tid;
         const int cell = a / p.A;
-        sc[q] = a < p.NA ? __ldg(sc_img + (size_t)a + (size_t)cell * p.A) : 0.f;   // cell*2A + A + an
+        sc[q] = a < a_hi ? __ldg(sc_img + (size_t)a + (size_t)cell * p.A) : 0.f;   // cell*2A + A + an
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int a = a0 + q * PT + tid;
-        if (a < p.NA) s_keys[a] = orderable_key(sc[q]);
+        if (a < a_hi) {
+          const unsigned key = orderable_key(sc[q]);
+#pragma unroll
+          for (int r = 0; r < CS; ++r) peer_keys[r][a] = key;
+        }
       }
     }
     if (p.decoded && writer)                  // the intermediate of :116-119, only when asked for
       for (int a = tid; a < p.NA; a += PT)
         reinterpret_cast<float4*>(p.decoded)[(size_t)img * p.NA + a] = decode_anchor(p, img, a, im_h, im_w);
   }
-  __syncthreads();
+  if constexpr (CS > 1) cg::this_cluster().sync();
+  else __syncthreads();
 
   // ---- phases 2-4: batches of M anchors in descending score order; decode + filter the batch;
   // keep-list NMS over its valid boxes
