@@ -1023,7 +1023,7 @@ cudaError_t wssdl_roi::launch_fwd_bins(const BinsPlan& p, const float* bottom, c
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     use_tma = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(bottom), gdim, gstr,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   }
   const bool linear = (C % 128 == 0);
   PoolArgs a;
