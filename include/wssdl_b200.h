@@ -64,7 +64,10 @@ enum {
   WSSDL_TUNE_PDL = 6,               /* programmatic dependent launch between the kernels of one
                                        call (pre-pass -> pooling, proposals -> pre-pass): 1 on
                                        (default), 0 off */
-  WSSDL_TUNE_COUNT = 7
+  WSSDL_TUNE_ROI_FWD_BALANCED = 7,  /* sorted bins: row bands that own equal shares of the map's
+                                       rows (taller bands): -1 when the grid is long (default),
+                                       0 shortest bands, 1 on                                    */
+  WSSDL_TUNE_COUNT = 8
 };
 int wssdl_set_tuning(int key, int value);
 int wssdl_get_tuning(int key);

@@ -74,10 +74,21 @@ def _plan(B, H, W, C, R, PH, PW, ws=True, force=0):
 
 
 def test_fwd_kernel_choice_on_the_baseline_shapes():
-    # C4 (the bench workload): sorted-bins kernel, two bands of 23 rows, RoI lists from the
-    # workspace
+    # C4 (the bench workload): sorted-bins kernel, two bands that own 19 rows each (27 resident
+    # rows: equal shares), RoI lists from the workspace; the shortest bands (23 rows, owning 15 and
+    # 23) through the tuning key
     p = _plan(256, 38, 50, 512, 256 * 300, 7, 7)
-    assert (p["kernel"], p["NB"], p["Hb"], p["step"], p["scan"]) == (SORTED, 2, 23, 15, 0)
+    assert (p["kernel"], p["NB"], p["Hb"], p["step"], p["scan"]) == (SORTED, 2, 27, 19, 0)
+    from wssdl_bus_b200 import _lib
+    prev = _lib.set_tuning("roi_fwd_balanced", 0)
+    try:
+        p = _plan(256, 38, 50, 512, 256 * 300, 7, 7)
+        assert (p["kernel"], p["NB"], p["Hb"], p["step"]) == (SORTED, 2, 23, 15)
+    finally:
+        _lib.set_tuning("roi_fwd_balanced", prev)
+    # short grids (a rank's 32 images at N = 8) keep the shortest bands
+    p = _plan(32, 38, 50, 512, 32 * 300, 7, 7)
+    assert (p["NB"], p["Hb"], p["step"]) == (2, 23, 15)
     # C1 / C2 (one image): one wave of the band kernel (a single launch), lists built in-kernel
     for R in (300, 128):
         p = _plan(1, 38, 50, 512, R, 7, 7)

@@ -110,7 +110,8 @@ def lib():
 
 # wssdl_set_tuning keys / values (include/wssdl_b200.h)
 TUNE_KEYS = {"roi_fwd_kernel": 0, "roi_fwd_slices": 1, "roi_fwd_chunks": 2, "nms_sweep_cluster": 3,
-             "proposals_cluster": 4, "roi_fwd_threads": 5, "pdl": 6}
+             "proposals_cluster": 4, "roi_fwd_threads": 5, "pdl": 6,
+             "roi_fwd_balanced": 7}
 ROI_FWD_KERNELS = {"auto": 0, "direct": 1, "tiled": 2, "band": 3, "sorted": 4}
 
 

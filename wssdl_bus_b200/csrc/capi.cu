@@ -32,6 +32,7 @@ void init_tuning() {
   g_tuning[WSSDL_TUNE_PROPOSALS_CLUSTER] = env_choice("WSSDL_PROPOSALS_CLUSTER", -1);
   g_tuning[WSSDL_TUNE_ROI_FWD_THREADS] = env_choice("WSSDL_ROI_FWD_THREADS", 0);
   g_tuning[WSSDL_TUNE_PDL] = env_choice("WSSDL_PDL", 1);
+  g_tuning[WSSDL_TUNE_ROI_FWD_BALANCED] = env_choice("WSSDL_ROI_FWD_BALANCED", -1);
 }
 }  // namespace
 

@@ -912,6 +912,22 @@ BinsPlan wssdl_roi::plan_bins(int B, int H, int W, int C, int R, int PH, int PW,
     p.g.NB = (int)((H - ov + (hb_max - ov) - 1) / (hb_max - ov));
     p.g.step = (H - ov + p.g.NB - 1) / p.g.NB;
     p.g.Hb = p.g.step + ov;
+    // A band OWNS the bins whose first row falls into its `step` rows, the last band also those of
+    // the ov rows behind: with the shortest bands (above) the last band owns step + ov rows
+    // (38 x 50: 15 and 23).  Equal shares (step = H / NB, 19 and 19) need ov more resident rows;
+    // taken when they still leave room for the records and the grid is long -- measured on C4:
+    // 256 images 3.012 -> 2.966 ms, 128 images 1.505 -> 1.492, but 64 images 0.805 -> 0.822 and
+    // 32 images 0.403 -> 0.416 (taller bands wait longer for their copy, and with few waves the
+    // equal CTAs end together) -- WSSDL_TUNE_ROI_FWD_BALANCED: -1 by grid size, 0 off, 1 on.
+    const int step_eq = (H + p.g.NB - 1) / p.g.NB;
+    const int btune = wssdl_tuning(WSSDL_TUNE_ROI_FWD_BALANCED);
+    const long long ctas2 = (long long)(C / N_SLICE) * p.g.NB * 2 * (B > 0 ? B : 1);
+    const bool balanced = btune > 0 || (btune < 0 && ctas2 >= 32ll * WSSDL_NUM_SMS);
+    if (balanced && step_eq + ov <= hb_max &&
+        budget - row_bytes * (size_t)(step_eq + ov) >= (size_t)48 * 1024) {
+      p.g.step = step_eq;
+      p.g.Hb = step_eq + ov;
+    }
   }
   if (p.g.NB > NB_MAX || (size_t)p.g.Hb * W > 2047) return p;   // first-cell field: 11 bits
   // the records of a CTA's range of groups take what the band leaves: at most one band's worth
