@@ -304,7 +304,7 @@ def run_ours(args):
             return p
 
         if pipelined:
-            php = PipelinedHotPath(hot, n_img, device=dev, gather=world > 1)
+            php = PipelinedHotPath(hot, n_img, device=dev, gather=world > 1, inputs_static=True)
             marks = {k: (tev(), tev(), tev(), tev()) for k in marked}
 
             def step(k=None):                         # noqa: F811
@@ -340,12 +340,32 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    pipelined = args.pipelined == 1 or (args.pipelined < 0 and B <= 64)
+    # Mode of the timed steps.  --pipelined -1 (default): ranks with at most 64 images try both
+    # modes for a few untimed steps and keep the faster one, all ranks agreeing on the slowest
+    # rank's times: pipelining hides the proposals' latency, but it issues its three kernels from
+    # two streams with more host work per step, and at 0.4 ms per step a busy host (8 ranks on one
+    # box) can make it the slower choice.
+    serial_ms = None
+    probe = None
+    if args.pipelined >= 0:
+        pipelined = args.pipelined == 1
+    elif B > 64:
+        pipelined = False
+    else:
+        n_probe = 10
+        t_pipe = device_leg(B, seeds, n_probe, pipelined=True)[0] / n_probe
+        t_ser = device_leg(B, seeds, n_probe, pipelined=False)[0] / n_probe
+        tt = torch.tensor([t_pipe, t_ser], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_pipe, t_ser = (float(v) for v in tt.tolist())
+        pipelined = t_pipe < t_ser
+        probe = {"pipelined_ms_per_step": t_pipe, "serial_ms_per_step": t_ser, "steps": n_probe}
+        serial_ms = t_ser
     ms_total, roi_ms, prop_ms, counts, d = device_leg(B, seeds, K, pipelined=pipelined)
     clocks = sampler.summary() if sampler else None
     # the latency of ONE step (fused call, nothing overlapped) next to the pipelined throughput
-    serial_ms = None
-    if pipelined:
+    if pipelined and serial_ms is None:
         lat = device_leg(B, seeds, max(3, min(K, 10)), pipelined=False)
         serial_ms = lat[0] / max(3, min(K, 10))
         del lat
@@ -436,6 +456,7 @@ def run_ours(args):
             # proposals_kernel + the RoI-pool kernels of one wssdl_hot_path_fwd call, per step
             "gpu_launches": (1 + roi_launches) * K,
             "pipelined": bool(pipelined),
+            "mode_probe": probe,
             "clocks": clocks,
             "rois_per_image": [int(counts.min()), int(counts.max())],
             "numa_node_rank0": numa,
@@ -497,9 +518,9 @@ def main():
     ap.add_argument("--no-weak", action="store_true")
     ap.add_argument("--pipelined", type=int, default=-1,
                     help="1: consecutive steps overlap on two streams (PipelinedHotPath); 0: one fused "
-                         "call per step, steps one after the other; -1: pipelined when a rank's batch "
-                         "is at most 64 images (one image's proposals are latency bound and leave "
-                         "most SMs idle on small batches)")
+                         "call per step, steps one after the other; -1: ranks with at most 64 images "
+                         "try both for a few untimed steps and keep the faster (one image's proposals "
+                         "are latency bound and leave most SMs idle on small batches)")
     ap.add_argument("--e2e-chunk", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")

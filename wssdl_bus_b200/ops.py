@@ -395,7 +395,7 @@ def proposals(cls_prob, bbox_pred, im_info, base_anchors, feat_stride, pre_nms_t
             rois = torch.empty((B * post, 5), dtype=torch.float32, device=dev)
             scores = torch.empty((B * post,), dtype=torch.float32, device=dev)
             counts = torch.empty((B,), dtype=torch.int32, device=dev)
-        aidx = torch.empty((B * post,), dtype=torch.int32, device=dev)
+        aidx = None if pad_rows_invalid else torch.empty((B * post,), dtype=torch.int32, device=dev)
         decoded = (torch.empty((B, H * W * A, 4), dtype=torch.float32, device=dev)
                    if want_decoded else None)
         ws = _workspace(_lib.lib().wssdl_proposals_workspace_bytes(B, H, W, A, int(pre_nms_topN),

@@ -166,12 +166,18 @@ class PipelinedHotPath:
     untouched until the batch is done.  world_size > 1: the packed detections of every batch are
     all-gathered behind its proposals (one collective, on the communicator's stream)."""
 
-    def __init__(self, hot, n_images, device=None, depth=2, gather=False, group=None):
+    def __init__(self, hot, n_images, device=None, depth=2, gather=False, group=None,
+                 inputs_static=False):
+        """inputs_static: the inputs of every submit() are already complete when it is called (a
+        benchmark's resident tensors), so the proposals stream need not wait for the submitting
+        stream each time (one stream wait less per batch on the host)."""
         self.hot, self.n, self.depth = hot, int(n_images), int(depth)
+        self.inputs_static = bool(inputs_static)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.s_prop = torch.cuda.Stream(device=self.dev, priority=-1)
         self.s_pool = torch.cuda.Stream(device=self.dev)
         self.blobs = [DetectionBlob(self.n, hot.post, device=self.dev) for _ in range(self.depth)]
+        self.views = [b.views() for b in self.blobs]       # (computed once: six view ops each)
         self.pool_done = [None] * self.depth
         self.gather_work = [None] * self.depth
         self.gather, self.group = bool(gather), group
@@ -182,8 +188,8 @@ class PipelinedHotPath:
         proposals stream) and around the RoI-pool stage (on the pooling stream)."""
         hot, b = self.hot, self.k % self.depth
         blob = self.blobs[b]
-        cur = torch.cuda.current_stream(self.dev)
-        self.s_prop.wait_stream(cur)                       # inputs are ready
+        if self.k == 0 or not self.inputs_static:
+            self.s_prop.wait_stream(torch.cuda.current_stream(self.dev))   # inputs are ready
         with torch.cuda.stream(self.s_prop):
             if self.pool_done[b] is not None:
                 self.s_prop.wait_event(self.pool_done[b])  # slot b's RoIs have been pooled
@@ -193,7 +199,7 @@ class PipelinedHotPath:
             if marks:
                 marks[0].record()
             p = ops.proposals(cls_prob, bbox_pred, im_info, hot.base, hot.feat_stride, hot.pre,
-                              hot.post, hot.thresh, hot.min_size, out=blob.views(),
+                              hot.post, hot.thresh, hot.min_size, out=self.views[b],
                               pad_rows_invalid=True)
             if marks:
                 marks[1].record()
