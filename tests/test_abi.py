@@ -52,6 +52,29 @@ def test_binding_table_matches_header(built_lib):
     assert lib.wssdl_nms_workspace_bytes(0) > 0
 
 
+def test_tuning_keys_match_the_header(built_lib):
+    """The tuning ABI: the Python names map onto the header's enum values, every key can be
+    read and written without a GPU, unknown keys are rejected."""
+    text = open(os.path.join(ROOT, "include", "wssdl_b200.h")).read()
+    enum = dict((k.lower(), int(v)) for k, v in re.findall(r"WSSDL_TUNE_([A-Z_]+)\s*=\s*(\d+)", text))
+    count = enum.pop("count")
+    assert enum == built_lib.TUNE_KEYS and count == len(enum)
+    lib = built_lib.lib()
+    for name, key in enum.items():
+        prev = lib.wssdl_get_tuning(key)
+        assert lib.wssdl_set_tuning(key, prev) == built_lib.OK, name
+    assert lib.wssdl_set_tuning(count, 0) == built_lib.EINVAL
+    assert lib.wssdl_set_tuning(-1, 0) == built_lib.EINVAL
+    # the hot-path entries validate their sizes before any CUDA call
+    assert lib.wssdl_hot_path_fwd_workspace_bytes(256, 300, 7, 7) >= lib.wssdl_roi_pool_fwd_workspace_bytes(
+        256, 256 * 300, 7, 7)
+    args = [None] * 4 + [3, 1, 38, 50, 512, 9, None, 16, 6000]
+    assert lib.wssdl_hot_path_fwd(*args, 0, 0.7, 0, 16.0, 7, 7, 0.0625, 0, None, None, None, None, None,
+                                  None, 0, None, None) == built_lib.EINVAL      # post_nms_topN <= 0
+    assert lib.wssdl_roi_pool_fwd_grouped(None, None, -1, 1, 2, 2, 4, 7, 7, 0.0625, 0, None, None, None, 0,
+                                          None) == built_lib.EINVAL
+
+
 def test_argument_validation_without_gpu(built_lib):
     lib = built_lib.lib()
     # negative sizes / bad enums are rejected before any CUDA call
