@@ -229,7 +229,7 @@ def run_ours(args):
     import torch.distributed as dist
     from wssdl_bus_b200 import ops
     from wssdl_bus_b200.pipeline import (DetectionBlob, HostPipeline, HotPath, PipelinedHotPath,
-                                         bind_to_gpu_numa_node, shard_images)
+                                         agree_on_faster_mode, bind_to_gpu_numa_node, shard_images)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -279,8 +279,8 @@ def run_ours(args):
         warm_ready = tev()
         # per timed step: start, the boundary between the two stages (recorded INSIDE the fused
         # call by the C ABI, on the launching stream), end
-        # (at most five steps carry them: three event records per step cost ~2 % of a 0.46 ms step)
-        stride = max(1, (steps + 4) // 5)             # at most five marked steps
+        # (at most three steps carry them: three event records per step cost ~2 % of a 0.46 ms step)
+        stride = max(1, (steps + 2) // 3)             # at most three marked steps
         marked = [k for k in range(steps) if k % stride == 0]
         marks = {k: (tev(), tev(), tev()) for k in marked}
 
@@ -355,11 +355,7 @@ def run_ours(args):
         n_probe = 10
         t_pipe = device_leg(B, seeds, n_probe, pipelined=True)[0] / n_probe
         t_ser = device_leg(B, seeds, n_probe, pipelined=False)[0] / n_probe
-        tt = torch.tensor([t_pipe, t_ser], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_pipe, t_ser = (float(v) for v in tt.tolist())
-        pipelined = t_pipe < t_ser
+        pipelined, t_pipe, t_ser = agree_on_faster_mode(t_pipe, t_ser, device=dev)
         probe = {"pipelined_ms_per_step": t_pipe, "serial_ms_per_step": t_ser, "steps": n_probe}
         serial_ms = t_ser
     ms_total, roi_ms, prop_ms, counts, d = device_leg(B, seeds, K, pipelined=pipelined)
@@ -444,7 +440,7 @@ def run_ours(args):
                          "ms_per_launch": r["roi_ms"],
                          "note": "ms_per_launch covers the whole RoI-pool stage of one rank (bin sort "
                                  "pre-pass + pooling kernel) in the timed steps that carry events "
-                                 "(at most five, evenly spaced): from the event "
+                                 "(at most three, evenly spaced): from the event "
                                  "wssdl_hot_path_fwd records on the launching stream between its "
                                  "two stages to an event behind the call"},
             "kernels_ms_per_step": {"proposals_kernel": r["prop_ms"], "roi_pool_fwd": r["roi_ms"],

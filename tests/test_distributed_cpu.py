@@ -21,8 +21,8 @@ def _worker(rank, world, port, n_images, post, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from wssdl_bus_b200.pipeline import (DetectionBlob, all_gather_blobs, all_gather_detections,
-                                         shard_images, unshard_detections)
+    from wssdl_bus_b200.pipeline import (DetectionBlob, agree_on_faster_mode, all_gather_blobs,
+                                         all_gather_detections, shard_images, unshard_detections)
     mine = shard_images(n_images, rank, world)
     n_local = (n_images + world - 1) // world
     det = torch.zeros((n_local, post, 5))
@@ -60,6 +60,12 @@ def _worker(rank, world, port, n_images, post, ret):
         ok = ok and torch.equal(b4, boxes) and torch.equal(s4, scores) and torch.equal(c4, counts)
         d4, cc4 = unshard_detections(b4, c4, n_images)
         ok = ok and torch.equal(d4, d) and torch.equal(cc4, c)
+    # bench.py's mode probe: the ranks measured different times and must all pick the same mode,
+    # decided on the slowest rank's (rank 1 finds pipelining slower: everybody runs fused steps)
+    pick, tp, tf = agree_on_faster_mode(0.42 if rank == 0 else 0.51, 0.46 if rank == 0 else 0.49)
+    ok = ok and (pick, tp, tf) == (False, 0.51, 0.49)
+    pick, tp, tf = agree_on_faster_mode(0.42 + 0.01 * rank, 0.46)
+    ok = ok and (pick, tp, tf) == (True, 0.43, 0.46)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

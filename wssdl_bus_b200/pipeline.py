@@ -234,6 +234,20 @@ class PipelinedHotPath:
         cur.wait_stream(self.s_prop)
 
 
+def agree_on_faster_mode(t_pipelined_ms, t_fused_ms, device=None, group=None):
+    """Every rank passes ITS measured step times of the two ways to run the hot path
+    (PipelinedHotPath / one fused call per step); all ranks get the same answer, decided on the
+    slowest rank's times (one all-reduce): (pipelined_is_faster, t_pipelined_ms, t_fused_ms).
+    A collective every rank has to call."""
+    import torch.distributed as dist
+    tt = torch.tensor([float(t_pipelined_ms), float(t_fused_ms)], dtype=torch.float64,
+                      device=device if device is not None else "cpu")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=group)
+    a, b = (float(v) for v in tt.tolist())
+    return a < b, a, b
+
+
 def all_gather_blobs(tensors, group=None, async_op=False):
     """all_gather_into_tensor of several [n_local, ...] tensors (NCCL over NVLink on GPUs,
     gloo in the CPU tests): -> list of [world, n_local, ...].
