@@ -18,5 +18,7 @@ Pieces
                    pinned by tests/golden/reference_layers_golden.npz: outputs of the
                    reference's own layer code run under a mechanical py2->py3 shim
                    (tests/golden/make_layers_golden.py).
+  oracle.philox    numpy Philox4x32-10 + the two selection rules of the device-side subsampling
+                   mode of the target layers (pinned by Random123's known-answer vectors).
 """
-from . import clib, layers, ref  # noqa: F401
+from . import clib, layers, philox, ref  # noqa: F401

@@ -220,6 +220,13 @@ def test_anchor_targets_device_sampler_philox(oracle_mod):
         assert not ow[b][lab4 < 0].any()
     assert drew >= 2                                      # the sampler actually had to draw
     assert not np.array_equal(lab[0], lab[2]) or not np.array_equal(pre[0], pre[2])
+    # the documented stream (include/wssdl_b200.h): the numpy restatement of the Philox selection
+    # (oracle/philox.py, pinned by Random123's known-answer vectors) gives the same labels, exactly
+    flat = labels_pre.cpu().numpy()
+    for b in range(B):
+        want = oracle_mod.philox.anchor_subsample(flat[b], b, 1234, num_fg, cfg.TRAIN.RPN_BATCHSIZE)
+        want = want.reshape(H, W, A).transpose(2, 0, 1).reshape(1, A * H, W)
+        assert np.array_equal(lab[b], want), b
 
 
 def test_proposal_targets_device_sampler_philox(oracle_mod):
@@ -274,6 +281,9 @@ def test_proposal_targets_device_sampler_philox(oracle_mod):
             assert not row_t[[k for k in range(K) if k != c or c == 0]].any()
         assert np.array_equal(ow, (iw > 0).astype(np.float32))
         assert not r[i * S + nf + nb:(i + 1) * S].any() and not t[i * S + nf + nb:(i + 1) * S].any()
+        # the documented stream: exactly the rows, in the order, the numpy restatement selects
+        sel_fg, sel_bg = oracle_mod.philox.roi_select(fg.size, bg.size, i, 9, fgq, S)
+        assert np.array_equal(idx, np.concatenate((fg[sel_fg], bg[sel_bg]))), i
     again = ptl.proposal_target_layer(rois, gt, num, K, True, False, sampler="philox", seed=9)
     assert np.array_equal(again[0], r) and np.array_equal(again[2], t)
     other = ptl.proposal_target_layer(rois, gt, num, K, True, False, sampler="philox", seed=10)

@@ -605,3 +605,29 @@ def test_reference_cuda_nms_host_build_agrees_with_its_python_twin(oracle_mod, g
         d = syn.dets(seed, n, **kw)
         for t in (0.3, 0.5, 0.7):
             assert [int(k) for k in ref.gpu_nms(d, t)] == [int(k) for k in m.py_cpu_nms(d, t)]
+
+
+def test_philox_restatement_against_random123_known_answers():
+    """oracle/philox.py: Philox4x32-10 against the known-answer vectors Random123 publishes
+    (kat_vectors: zeros, all ones, digits of pi), and the selection helpers' basic properties."""
+    from oracle import philox as ph
+    kat = (((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)))
+    for ctr, key, want in kat:
+        got = tuple(int(np.asarray(v).reshape(-1)[0]) for v in ph.philox4x32_10(*ctr, *key))
+        assert got == want
+    # vectorised counters give the scalar results
+    v = ph.philox4x32_10(np.arange(5), 7, 1, 0, 123, 456)
+    for i in range(5):
+        assert tuple(int(a[i]) for a in v) == tuple(
+            int(np.asarray(a).reshape(-1)[0]) for a in ph.philox4x32_10(i, 7, 1, 0, 123, 456))
+    labels = np.array([1] * 10 + [0] * 20 + [-1] * 5, np.float32)
+    out = ph.anchor_subsample(labels, 0, 42, num_fg=4, batchsize=12)
+    assert (out == 1).sum() == 4 and (out == 0).sum() == 8 and np.all(out[labels == -1] == -1)
+    assert np.all(labels[out == 1] == 1) and np.all(labels[out == 0] == 0)
+    f, b = ph.roi_select(10, 50, 1, 42, 4, 16)
+    assert len(f) == 4 and len(b) == 12 and len(set(f)) == 4 and len(set(b)) == 12
+    assert np.array_equal(ph.roi_select(10, 50, 1, 42, 4, 16)[1], b)
+    assert not np.array_equal(ph.roi_select(10, 50, 2, 42, 4, 16)[1], b)
